@@ -1,0 +1,77 @@
+"""Builds the committed golden fixtures from the reference's own artefacts.
+
+Run once in the build container (where /root/reference is mounted):
+
+    python tests/golden/make_golden.py
+
+Outputs (committed; /root/reference does not exist on the GPU box):
+  tests/golden/ref_clean_pairs.npz  -- a spread of the reference's
+      ``clear_audio/<stem>.wav`` (int16 PCM) with the matching committed
+      ``cache_features/<stem>_clean_feats.npy`` (float32[149]); the feature function's
+      golden input/output pairs.
+  tests/golden/ref_scaler_after.npz -- X_after (the 905x149 matrix the reference fed to
+      ``StandardScaler().fit`` at pipeline1.py:471, rebuilt from cache_features/ in
+      sorted-path order, duplicates included) with mean_/var_/scale_ unpickled from
+      output_results/scaler_after.pkl.
+Only data is copied, never reference source code.
+"""
+import glob
+import os
+import pickle
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", ".."))
+from oracle import wavio  # noqa: E402
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def main():
+    feats = sorted(glob.glob(f"{REF}/cache_features/*_clean_feats.npy"))
+    stems = [os.path.basename(f)[:-len("_clean_feats.npy")] for f in feats]
+    lens = []
+    for s in stems:
+        q, sr = wavio.read_wav_pcm16(f"{REF}/clear_audio/{s}.wav")
+        assert sr == 16000
+        lens.append(len(q))
+    order = np.argsort(lens)
+    # shortest, longest and an even spread in between, total audio kept small (~1.7 MB)
+    picks = sorted(set([order[0], order[1], order[-1], order[-2]] +
+                       [order[int(round(i))] for i in np.linspace(0, len(order) - 1, 22)]))
+    pcm, offs, gold, names = [], [0], [], []
+    for i in picks:
+        q, _ = wavio.read_wav_pcm16(f"{REF}/clear_audio/{stems[i]}.wav")
+        pcm.append(q)
+        offs.append(offs[-1] + len(q))
+        gold.append(np.load(feats[i]))
+        names.append(stems[i])
+    np.savez_compressed(os.path.join(HERE, "ref_clean_pairs.npz"), pcm=np.concatenate(pcm),
+                        offsets=np.asarray(offs, dtype=np.int64), feats=np.stack(gold),
+                        names=np.asarray(names))
+    print("pairs:", len(picks), "samples:", offs[-1], "lens:", [lens[i] for i in picks])
+
+    # scaler golden: rows follow sorted(list_audio_files) (pipeline1.py:91-97), key = basename stem
+    files = []
+    for r, _, fs in os.walk(f"{REF}/segrigated_samples"):
+        for f in fs:
+            if f.lower().endswith((".wav", ".mp3", ".flac", ".m4a", ".ogg")):
+                files.append(os.path.join(r, f))
+    files = sorted(files)
+    rows = [np.load(f"{REF}/cache_features/{os.path.basename(p).rsplit('.', 1)[0]}_clean_feats.npy") for p in files]
+    X = np.vstack(rows)
+    with open(f"{REF}/output_results/scaler_after.pkl", "rb") as fh:
+        try:
+            sc = pickle.load(fh)
+        except Exception:
+            import joblib
+            sc = joblib.load(f"{REF}/output_results/scaler_after.pkl")
+    np.savez_compressed(os.path.join(HERE, "ref_scaler_after.npz"), X=X, mean=sc.mean_, var=sc.var_,
+                        scale=sc.scale_, n=np.int64(sc.n_samples_seen_))
+    print("scaler rows:", X.shape, "n_samples_seen:", sc.n_samples_seen_)
+
+
+if __name__ == "__main__":
+    main()
