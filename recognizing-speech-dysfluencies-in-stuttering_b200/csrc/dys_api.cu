@@ -1,0 +1,318 @@
+// C ABI of libdysb200.so (declared in include/dysfluency_b200.h): argument checks, workspace
+// carving, sub-batch loops.  No host copies, no CPU fallback.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/dysfluency_b200.h"
+#include "dys_error.h"
+#include "dys_kernels.h"
+
+namespace dys {
+
+namespace {
+thread_local std::string g_err;
+}
+void set_error(const std::string& msg) { g_err = msg; }
+const char* last_error_cstr() { return g_err.c_str(); }
+
+namespace {
+
+size_t al256(size_t b) { return (b + 255) & ~size_t(255); }
+
+int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    if (!v || !*v) return dflt;
+    const long x = std::strtol(v, nullptr, 10);
+    return x > 0 ? int(x) : dflt;
+}
+// Sub-batch caps: how many clip instances / denoise chunks share one scratch arena per launch group.
+int feat_cap() { return env_int("DYS_FEAT_SUBBATCH", 1024); }
+int nr_cap() { return env_int("DYS_NR_SUBBATCH", 1024); }
+
+struct Layout {
+    int64_t clean_pitch = 0;
+    size_t clean_off = 0, peak_off = 0, flag_off = 0, scratch_off = 0;
+    int t_max = 0, ta_max = 0, cpc = 1;
+};
+
+Layout make_layout(int n_clips, int max_len, bool with_clean) {
+    Layout L;
+    L.t_max = frames_of(std::max(max_len, 0));
+    L.ta_max = nr_ta_max(std::max(max_len, 1));
+    L.cpc = nr_chunks_of(std::max(max_len, 1));
+    size_t off = 0;
+    if (with_clean) {
+        L.clean_pitch = (int64_t(std::max(max_len, 1)) + 63) & ~int64_t(63);
+        L.clean_off = off; off += al256(size_t(n_clips) * L.clean_pitch * 4);
+        L.peak_off = off; off += al256(size_t(n_clips) * 4);
+        L.flag_off = off; off += al256(size_t(n_clips) * 4);
+    }
+    L.scratch_off = off;
+    return L;
+}
+
+int check_common(const void* d_audio, const void* d_starts, const void* d_lengths, int n_clips, int max_len) {
+    if (n_clips < 0 || max_len < 0) { set_error("n_clips and max_len must be >= 0"); return DYS_ERR_INVALID; }
+    if (n_clips > 0 && (!d_audio || !d_starts || !d_lengths)) { set_error("null device pointer"); return DYS_ERR_INVALID; }
+    if (int64_t(n_clips) * 2 > 0x7fff0000LL) { set_error("too many clips for one call"); return DYS_ERR_INVALID; }
+    return DYS_OK;
+}
+
+int run_features(const DeviceTables& tb, const ClipView& cv, int n_inst_total, const Layout& L, unsigned char* ws,
+                 size_t ws_bytes, float* out_raw, float* out_clean, int32_t* status, cudaStream_t stream) {
+    const size_t avail = ws_bytes - L.scratch_off;
+    const size_t per = feat_scratch_bytes(1, L.t_max);
+    int n_sub = int(std::min<size_t>(avail / per, size_t(feat_cap())));
+    n_sub = std::min(n_sub, n_inst_total);
+    if (n_sub < 1) { set_error("workspace too small for one clip"); return DYS_ERR_WORKSPACE; }
+    while (n_sub > 1 && feat_scratch_bytes(n_sub, L.t_max) > avail) --n_sub;
+    FeatScratch sc;
+    feat_scratch_carve(ws + L.scratch_off, n_sub, L.t_max, &sc);
+    for (int i0 = 0; i0 < n_inst_total; i0 += n_sub) {
+        const int cnt = std::min(n_sub, n_inst_total - i0);
+        DYS_CUDA_OK(launch_features(tb, cv, i0, cnt, sc, out_raw, out_clean, status, stream));
+    }
+    return DYS_OK;
+}
+
+}  // namespace
+}  // namespace dys
+
+using namespace dys;
+
+extern "C" {
+
+DYS_API int dys_version(void) { return 100; }
+
+DYS_API const char* dys_last_error(void) { return last_error_cstr(); }
+
+DYS_API int dys_init(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        set_error("no CUDA device: this library has no CPU path");
+        return DYS_ERR_CUDA;
+    }
+    return device_tables() ? DYS_OK : DYS_ERR_CUDA;
+}
+
+DYS_API int64_t dys_workspace_bytes(int32_t n_clips, int32_t max_len, int32_t with_clean) {
+    if (n_clips < 0 || max_len < 0) return -1;
+    const Layout L = make_layout(n_clips, max_len, with_clean != 0);
+    const int n_inst = std::max(1, std::min(feat_cap(), n_clips * (with_clean ? 2 : 1)));
+    size_t scratch = feat_scratch_bytes(n_inst, L.t_max);
+    if (with_clean) {
+        const int n_items = std::max(1, std::min(nr_cap(), n_clips * L.cpc));
+        scratch = std::max(scratch, nr_scratch_bytes(n_items, L.ta_max));
+    }
+    return int64_t(L.scratch_off + scratch);
+}
+
+DYS_API int64_t dys_workspace_min_bytes(int32_t n_clips, int32_t max_len, int32_t with_clean) {
+    if (n_clips < 0 || max_len < 0) return -1;
+    const Layout L = make_layout(n_clips, max_len, with_clean != 0);
+    size_t scratch = feat_scratch_bytes(1, L.t_max);
+    if (with_clean) scratch = std::max(scratch, nr_scratch_bytes(1, L.ta_max));
+    return int64_t(L.scratch_off + scratch);
+}
+
+DYS_API int dys_features_raw(const float* d_audio, const int64_t* d_starts, const int32_t* d_lengths, int32_t n_clips,
+                     int32_t max_len, float* d_out, int32_t* d_status, void* d_workspace, int64_t workspace_bytes,
+                     void* stream) {
+    if (int rc = check_common(d_audio, d_starts, d_lengths, n_clips, max_len)) return rc;
+    if (n_clips == 0) return DYS_OK;
+    if (!d_out || !d_status || !d_workspace) { set_error("null output / workspace pointer"); return DYS_ERR_INVALID; }
+    const DeviceTables* tb = device_tables();
+    if (!tb) return DYS_ERR_CUDA;
+    const Layout L = make_layout(n_clips, max_len, false);
+    if (workspace_bytes < dys_workspace_min_bytes(n_clips, max_len, 0)) {
+        set_error("workspace smaller than dys_workspace_min_bytes()");
+        return DYS_ERR_WORKSPACE;
+    }
+    ClipView cv{};
+    cv.audio = d_audio; cv.starts = d_starts; cv.lengths = d_lengths; cv.n_clips = n_clips; cv.max_len = max_len;
+    return run_features(*tb, cv, n_clips, L, static_cast<unsigned char*>(d_workspace), size_t(workspace_bytes), d_out,
+                        nullptr, d_status, static_cast<cudaStream_t>(stream));
+}
+
+DYS_API int dys_features_raw_clean(const float* d_audio, const int64_t* d_starts, const int32_t* d_lengths, int32_t n_clips,
+                           int32_t max_len, float prop_decrease, float* d_out_raw, float* d_out_clean,
+                           int32_t* d_status, int16_t* d_clean_pcm, const int64_t* d_pcm_starts, void* d_workspace,
+                           int64_t workspace_bytes, void* stream) {
+    if (int rc = check_common(d_audio, d_starts, d_lengths, n_clips, max_len)) return rc;
+    if (n_clips == 0) return DYS_OK;
+    if (!d_out_raw || !d_out_clean || !d_status || !d_workspace) {
+        set_error("null output / workspace pointer");
+        return DYS_ERR_INVALID;
+    }
+    if (d_clean_pcm && !d_pcm_starts) { set_error("d_clean_pcm given without d_pcm_starts"); return DYS_ERR_INVALID; }
+    if (!(prop_decrease >= 0.f && prop_decrease <= 1.f)) { set_error("prop_decrease must be in [0, 1]"); return DYS_ERR_INVALID; }
+    const DeviceTables* tb = device_tables();
+    if (!tb) return DYS_ERR_CUDA;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const Layout L = make_layout(n_clips, max_len, true);
+    if (workspace_bytes < dys_workspace_min_bytes(n_clips, max_len, 1)) {
+        set_error("workspace smaller than dys_workspace_min_bytes()");
+        return DYS_ERR_WORKSPACE;
+    }
+    unsigned char* ws = static_cast<unsigned char*>(d_workspace);
+    float* clean = reinterpret_cast<float*>(ws + L.clean_off);
+    float* peak = reinterpret_cast<float*>(ws + L.peak_off);
+    int32_t* flag = reinterpret_cast<int32_t*>(ws + L.flag_off);
+    ClipView cv{};
+    cv.audio = d_audio; cv.starts = d_starts; cv.lengths = d_lengths; cv.n_clips = n_clips; cv.max_len = max_len;
+    cv.clean = clean; cv.clean_pitch = L.clean_pitch; cv.clean_peak = peak; cv.clean_flag = flag;
+
+    // ---- spectral gate over sub-batches of chunks ------------------------------------------
+    DYS_CUDA_OK(launch_clean_init(cv, peak, flag, st));
+    {
+        const size_t avail = size_t(workspace_bytes) - L.scratch_off;
+        const size_t per = nr_scratch_bytes(1, L.ta_max);
+        const int64_t n_items = int64_t(n_clips) * L.cpc;
+        int n_sub = int(std::min<size_t>(avail / per, size_t(nr_cap())));
+        n_sub = int(std::min<int64_t>(n_sub, n_items));
+        if (n_sub < 1) { set_error("workspace too small for one denoise chunk"); return DYS_ERR_WORKSPACE; }
+        while (n_sub > 1 && nr_scratch_bytes(n_sub, L.ta_max) > avail) --n_sub;
+        NrScratch sc;
+        nr_scratch_carve(ws + L.scratch_off, n_sub, L.ta_max, &sc);
+        for (int64_t i0 = 0; i0 < n_items; i0 += n_sub) {
+            const int cnt = int(std::min<int64_t>(n_sub, n_items - i0));
+            DYS_CUDA_OK(launch_denoise(*tb, cv, clean, peak, flag, L.cpc, int(i0), cnt, sc, prop_decrease, st));
+        }
+    }
+    if (d_clean_pcm) DYS_CUDA_OK(launch_quantize_pcm(cv, d_clean_pcm, d_pcm_starts, st));
+    // ---- features of both branches ----------------------------------------------------------
+    return run_features(*tb, cv, 2 * n_clips, L, ws, size_t(workspace_bytes), d_out_raw, d_out_clean, d_status, st);
+}
+
+DYS_API int dys_cmvn_accumulate(const float* d_feats, int64_t n_rows, const double* d_shift, double* d_acc, double* d_partials,
+                        void* stream) {
+    if (n_rows < 0 || !d_acc || !d_partials || (n_rows > 0 && !d_feats)) { set_error("bad cmvn arguments"); return DYS_ERR_INVALID; }
+    DYS_CUDA_OK(launch_cmvn_accumulate(d_feats, n_rows, d_shift, d_acc, d_partials, static_cast<cudaStream_t>(stream)));
+    return DYS_OK;
+}
+
+DYS_API int dys_cmvn_finalize(const double* d_acc, const double* d_shift, double* d_mean, double* d_scale, void* stream) {
+    if (!d_acc || !d_mean || !d_scale) { set_error("bad cmvn arguments"); return DYS_ERR_INVALID; }
+    DYS_CUDA_OK(launch_cmvn_finalize(d_acc, d_shift, d_mean, d_scale, static_cast<cudaStream_t>(stream)));
+    return DYS_OK;
+}
+
+DYS_API int dys_cmvn_apply(const float* d_feats, int64_t n_rows, const double* d_mean, const double* d_scale, float* d_out,
+                   void* stream) {
+    if (n_rows < 0 || !d_mean || !d_scale || (n_rows > 0 && (!d_feats || !d_out))) { set_error("bad cmvn arguments"); return DYS_ERR_INVALID; }
+    DYS_CUDA_OK(launch_cmvn_apply(d_feats, n_rows, d_mean, d_scale, d_out, static_cast<cudaStream_t>(stream)));
+    return DYS_OK;
+}
+
+DYS_API int64_t dys_get_table(int32_t which, int32_t arg, void* h_out, int64_t max_elems) {
+    const HostTables& h = host_tables();
+    const void* src = nullptr;
+    int64_t n = 0;
+    size_t esz = 4;
+    double taps[kNrFreqTaps + kNrTimeTaps];
+    switch (which) {
+        case 0: src = h.mel_dense.data(); n = int64_t(h.mel_dense.size()); break;
+        case 1: src = h.dct.data(); n = int64_t(h.dct.size()); break;
+        case 2:
+            if (arg < 0 || arg >= kTunings) return -1;
+            src = h.chroma.data() + size_t(arg) * kBins * kChroma; n = kBins * kChroma; break;
+        case 3: src = h.hann2048.data(); n = kNfft; break;
+        case 4: src = h.tuning_edges.data(); n = kTunings + 1; esz = 8; break;
+        case 5:
+            std::copy(h.smooth_f.begin(), h.smooth_f.end(), taps);
+            std::copy(h.smooth_t.begin(), h.smooth_t.end(), taps + kNrFreqTaps);
+            src = taps; n = kNrFreqTaps + kNrTimeTaps; esz = 8; break;
+        case 6: src = h.wss.data(); n = kNrHop; esz = 8; break;
+        case 7: src = &h.iir_b; n = 1; esz = 8; break;
+        default: return -1;
+    }
+    if (!h_out || max_elems < n) return -1;
+    std::memcpy(h_out, src, size_t(n) * esz);
+    return n;
+}
+
+DYS_API int dys_debug_feature_stages(const float* d_audio, int32_t n, float* d_power, float* d_logmel, float* d_mfcc,
+                             float* d_chroma, int32_t* d_scalars, float* d_out, void* stream) {
+    if (!d_audio || n < 0) { set_error("bad debug arguments"); return DYS_ERR_INVALID; }
+    const DeviceTables* tb = device_tables();
+    if (!tb) return DYS_ERR_CUDA;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int T = frames_of(n);
+    unsigned char* ws = nullptr;
+    const size_t bytes = feat_scratch_bytes(1, T) + 4096;
+    DYS_CUDA_OK(cudaMalloc(&ws, bytes));
+    int64_t h_start = 0;
+    int32_t h_len = n;
+    int64_t* d_start = reinterpret_cast<int64_t*>(ws);
+    int32_t* d_len = reinterpret_cast<int32_t*>(ws + 64);
+    int32_t* d_status = reinterpret_cast<int32_t*>(ws + 128);
+    float* d_feat = reinterpret_cast<float*>(ws + 1024);
+    cudaMemcpyAsync(d_start, &h_start, 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_len, &h_len, 4, cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(ws + 4096, 0, bytes - 4096, st);
+    ClipView cv{};
+    cv.audio = d_audio; cv.starts = d_start; cv.lengths = d_len; cv.n_clips = 1; cv.max_len = n;
+    FeatScratch sc;
+    feat_scratch_carve(ws + 4096, 1, T, &sc);
+    cudaError_t e = launch_features(*tb, cv, 0, 1, sc, d_feat, nullptr, d_status, st);
+    if (e == cudaSuccess) {
+        if (d_power) cudaMemcpyAsync(d_power, sc.power, size_t(T) * kBinsPad * 4, cudaMemcpyDeviceToDevice, st);
+        if (d_logmel) cudaMemcpyAsync(d_logmel, sc.logmel, size_t(T) * kMels * 4, cudaMemcpyDeviceToDevice, st);
+        if (d_mfcc) cudaMemcpyAsync(d_mfcc, sc.mfcc, size_t(T) * kMfcc * 4, cudaMemcpyDeviceToDevice, st);
+        if (d_chroma) cudaMemcpyAsync(d_chroma, sc.chroma, size_t(T) * kChroma * 4, cudaMemcpyDeviceToDevice, st);
+        if (d_out) cudaMemcpyAsync(d_out, d_feat, kFeat * 4, cudaMemcpyDeviceToDevice, st);
+        if (d_scalars) {
+            cudaMemcpyAsync(d_scalars + 1, sc.tuning_idx, 4, cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync(d_scalars + 2, sc.peak_count, 4, cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync(d_scalars + 3, d_status, 4, cudaMemcpyDeviceToDevice, st);
+            cudaMemcpyAsync(d_scalars, &T, 4, cudaMemcpyHostToDevice, st);
+        }
+        e = cudaStreamSynchronize(st);
+    }
+    cudaFree(ws);
+    if (e != cudaSuccess) { set_error(std::string("debug_feature_stages: ") + cudaGetErrorString(e)); return DYS_ERR_CUDA; }
+    return DYS_OK;
+}
+
+DYS_API int dys_debug_denoise(const float* d_audio, int32_t n, float prop_decrease, float* d_clean, float* d_info, void* stream) {
+    if (!d_audio || n <= 0 || !d_clean) { set_error("bad debug arguments"); return DYS_ERR_INVALID; }
+    const DeviceTables* tb = device_tables();
+    if (!tb) return DYS_ERR_CUDA;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int cpc = nr_chunks_of(n), ta = nr_ta_max(n);
+    unsigned char* ws = nullptr;
+    const size_t bytes = nr_scratch_bytes(1, ta) + 4096;
+    DYS_CUDA_OK(cudaMalloc(&ws, bytes));
+    int64_t h_start = 0;
+    int32_t h_len = n;
+    int64_t* d_start = reinterpret_cast<int64_t*>(ws);
+    int32_t* d_len = reinterpret_cast<int32_t*>(ws + 64);
+    float* d_peak = reinterpret_cast<float*>(ws + 128);
+    int32_t* d_flag = reinterpret_cast<int32_t*>(ws + 192);
+    cudaMemcpyAsync(d_start, &h_start, 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_len, &h_len, 4, cudaMemcpyHostToDevice, st);
+    ClipView cv{};
+    cv.audio = d_audio; cv.starts = d_start; cv.lengths = d_len; cv.n_clips = 1; cv.max_len = n;
+    cv.clean = d_clean; cv.clean_pitch = n; cv.clean_peak = d_peak; cv.clean_flag = d_flag;
+    NrScratch sc;
+    nr_scratch_carve(ws + 4096, 1, ta, &sc);
+    cudaError_t e = launch_clean_init(cv, d_peak, d_flag, st);
+    for (int it = 0; it < cpc && e == cudaSuccess; ++it)
+        e = launch_denoise(*tb, cv, d_clean, d_peak, d_flag, cpc, it, 1, sc, prop_decrease, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess && d_info) {
+        float info[2];
+        int32_t flag = 0;
+        cudaMemcpy(&info[0], d_peak, 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(&flag, d_flag, 4, cudaMemcpyDeviceToHost);
+        info[1] = float(flag);
+        e = cudaMemcpy(d_info, info, 8, cudaMemcpyHostToDevice);
+    }
+    cudaFree(ws);
+    if (e != cudaSuccess) { set_error(std::string("debug_denoise: ") + cudaGetErrorString(e)); return DYS_ERR_CUDA; }
+    return DYS_OK;
+}
+
+}  // extern "C"

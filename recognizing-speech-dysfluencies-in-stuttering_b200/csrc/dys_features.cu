@@ -1,0 +1,535 @@
+// Feature kernels: 16 kHz clip -> float32[149]  (MFCC/delta/delta2/chroma statistics).
+//
+// Replaces extract_audio_features / extract_features of the reference
+// (/root/reference/pipeline1.py:206-265; identical copy main1.py:665-715), i.e. the librosa
+// call chain  feature.mfcc -> melspectrogram -> stft -> power_to_db -> dct,  feature.delta x2,
+// feature.chroma_stft -> estimate_tuning -> piptrack -> filters.chroma.
+//
+//   k_frame_spectra : one warp per STFT frame.  Samples are read once with coalesced 8-byte
+//                     loads (4x frame overlap is served by L1/L2), windowed, transformed by the
+//                     warp-resident 1024-point complex FFT (dys_fft.cuh), split into the 1025-bin
+//                     power spectrum, and -- while the frame is still in shared memory/registers --
+//                     reduced to 128 log-mel values and to the piptrack peak list.
+//   k_tuning        : one CTA per clip: exact median (radix select) of the peak magnitudes,
+//                     100-bin residual histogram, first arg-max  -> tuning index.
+//   k_frame_cepstra : one warp per frame: top-dB clamp + DCT-II (20x128) and the 12x1025 chroma
+//                     projection with the tuning's filterbank + inf-norm.
+//   k_clip_stats    : one CTA per clip: delta / delta-delta (Savitzky-Golay taps, replicated
+//                     edges) and mean / population std of every row -> the 149-vector.
+#include <cfloat>
+#include <cmath>
+
+#include "dys_fft.cuh"
+#include "dys_kernels.h"
+
+namespace dys {
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kFramesPerCta = 96;            // 12 frames per warp; one CTA covers a 3-s clip (94 frames)
+
+__device__ __forceinline__ int enc_f32(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float dec_f32(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// libsndfile float -> PCM-16 -> librosa.load: clip(lrintf(x * 32768)) / 32768   (pipeline1.py:142, :437)
+__device__ __forceinline__ float pcm16_roundtrip(float y, float peak) {
+    const float s = __fdiv_rn(y, peak) * 32768.0f;
+    float q = rintf(s);
+    q = fminf(fmaxf(q, -32768.0f), 32767.0f);
+    return q * (1.0f / 32768.0f);
+}
+
+struct InstSrc {
+    const float* base;   // first sample of the clip on this branch
+    int n;               // samples
+    float peak;          // > 0: apply normalise + PCM-16 round trip with this divisor; 0: plain samples
+    bool vec_ok;         // base is 8-byte aligned
+    bool check_finite;
+};
+
+__device__ __forceinline__ InstSrc inst_source(const ClipView& cv, int inst) {
+    InstSrc s;
+    const bool clean = inst >= cv.n_clips;
+    const int c = clean ? inst - cv.n_clips : inst;
+    int n = cv.lengths[c];
+    if (n < 0 || n > cv.max_len) n = 0;
+    s.n = n;
+    s.peak = 0.f;
+    s.check_finite = true;
+    s.base = cv.audio + cv.starts[c];
+    if (clean && cv.clean_flag[c] == 0) {
+        s.base = cv.clean + int64_t(c) * cv.clean_pitch;
+        float pk = cv.clean_peak[c];
+        if (pk < FLT_MIN) pk = 1.0f;             // librosa.util.normalize: below tiny -> left unscaled
+        s.peak = pk;
+        s.check_finite = false;
+    }
+    s.vec_ok = (reinterpret_cast<uintptr_t>(s.base) & 7u) == 0;
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void k_feat_init(int* peak_count, int* lmax_enc, int32_t* status, const ClipView cv, int inst0, int n_inst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_inst) return;
+    peak_count[i] = 0;
+    lmax_enc[i] = enc_f32(-INFINITY);
+    const int inst = inst0 + i;
+    const bool clean = inst >= cv.n_clips;
+    const int c = clean ? inst - cv.n_clips : inst;
+    const int n = cv.lengths[c];
+    int st = 0;
+    if (n < 0 || n > cv.max_len) st |= kStatusBadLength | kStatusShort;
+    else if (frames_of(n) < 9) st |= kStatusShort;
+    if (clean && cv.clean_flag[c] != 0) st |= kStatusCleanFallback;
+    status[inst] = st;
+}
+
+// ------------------------------------------------------------------------------------------
+struct SpectraSmem {
+    float hann[kNfft];
+    float2 tw[32 * 32];
+    float2 split[1024];
+    float mel_w[kMelNnz + 4];
+    int mel_start[kMels];
+    int mel_len[kMels];
+    int mel_ptr[kMels];
+    float2 xbuf[kWarps][kXbuf1024];
+};
+
+__global__ void __launch_bounds__(kThreads, 2)
+k_frame_spectra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch sc, int32_t* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SpectraSmem& sm = *reinterpret_cast<SpectraSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int li = blockIdx.x;                 // local instance
+    const int inst = inst0 + li;
+    const InstSrc src = inst_source(cv, inst);
+    const int T = frames_of(src.n);
+    const int t_begin = blockIdx.y * kFramesPerCta;
+    if (T < 9 || t_begin >= T) return;         // short clips emit zeros in k_clip_stats
+    const int t_end = min(T, t_begin + kFramesPerCta);
+
+    for (int i = tid; i < kNfft; i += kThreads) sm.hann[i] = tb.hann2048[i];
+    for (int i = tid; i < 1024; i += kThreads) { sm.tw[i] = tb.tw1024[i]; sm.split[i] = tb.split2048[i]; }
+    for (int i = tid; i < kMelNnz; i += kThreads) sm.mel_w[i] = tb.mel_w[i];
+    for (int i = tid; i < kMels; i += kThreads) {
+        sm.mel_start[i] = tb.mel_start[i]; sm.mel_len[i] = tb.mel_len[i]; sm.mel_ptr[i] = tb.mel_ptr[i];
+    }
+    __syncthreads();
+
+    float2* xbuf = sm.xbuf[warp];
+    float* pbuf = reinterpret_cast<float*>(xbuf);          // the warp's 1025-bin power spectrum (aliases the tile)
+    float* g_power = sc.power + size_t(li) * sc.t_max * kBinsPad;
+    float* g_logmel = sc.logmel + size_t(li) * sc.t_max * kMels;
+    float2* g_peaks = sc.peaks + size_t(li) * sc.t_max * kMaxPeaksPerFrame;
+    float warp_lmax = -INFINITY;
+    bool nonfinite = false;
+
+    for (int t = t_begin + warp; t < t_end; t += kWarps) {
+        // ---- load + window: z[j] = (x[2j], x[2j+1]) * hann, j = lane + 32 m ------------------
+        float2 v[32];
+        const int f0 = t * kHop - kNfft / 2;               // clip-relative index of the frame's first sample
+        static_for<32>([&](auto im) {
+            constexpr int m = decltype(im)::value;
+            const int j2 = 2 * (lane + 32 * m);
+            const int s = f0 + j2;
+            float a = 0.f, b = 0.f;
+            if (s >= 0 && s + 1 < src.n && src.vec_ok) {
+                const float2 p = __ldg(reinterpret_cast<const float2*>(src.base + s));
+                a = p.x; b = p.y;
+            } else {
+                if (s >= 0 && s < src.n) a = __ldg(src.base + s);
+                if (s + 1 >= 0 && s + 1 < src.n) b = __ldg(src.base + s + 1);
+            }
+            if (src.peak > 0.f) {
+                a = (s >= 0 && s < src.n) ? pcm16_roundtrip(a, src.peak) : 0.f;
+                b = (s + 1 >= 0 && s + 1 < src.n) ? pcm16_roundtrip(b, src.peak) : 0.f;
+            } else if (src.check_finite) {
+                nonfinite |= !(isfinite(a) && isfinite(b));
+            }
+            const float2 w = *reinterpret_cast<const float2*>(&sm.hann[j2]);
+            v[m] = make_float2(a * w.x, b * w.y);
+        });
+
+        warp_fft1024(v, xbuf, sm.tw, lane);
+
+        // ---- real split -> power spectrum P[k], k = lane + 32 q --------------------------------
+        // X[k] = (Z[k] + conj Z[1024-k]) / 2 - i e^{-2 pi i k / 2048} (Z[k] - conj Z[1024-k]) / 2 ;
+        // Z[1024-k] sits in lane (32 - lane) & 31, register 31 - q (lane 0: its own register (32 - q) & 31).
+        // The exchange tile is dead after the transposition, so P is written straight into it.
+        float* gp = g_power + size_t(t) * kBinsPad;
+        const int src_lane = (32 - lane) & 31;
+        float fmax_ = 0.f;
+        static_for<32>([&](auto iq) {
+            constexpr int q = decltype(iq)::value;
+            const int k = lane + 32 * q;
+            const float2 z = v[q];
+            float2 p;
+            p.x = __shfl_sync(0xffffffffu, v[31 - q].x, src_lane);
+            p.y = __shfl_sync(0xffffffffu, v[31 - q].y, src_lane);
+            if (lane == 0) p = v[(32 - q) & 31];
+            const float ex = z.x + p.x, ey = z.y - p.y, dx = z.x - p.x, dy = z.y + p.y;
+            const float2 cs = sm.split[k];
+            const float xr = ex + (cs.x * dy - cs.y * dx);
+            const float xi = ey - (cs.x * dx + cs.y * dy);
+            const float pw = 0.25f * (xr * xr + xi * xi);
+            fmax_ = fmaxf(fmax_, pw);
+            pbuf[k] = pw;
+            gp[k] = pw;
+        });
+        {
+            const float z0x = __shfl_sync(0xffffffffu, v[0].x, 0), z0y = __shfl_sync(0xffffffffu, v[0].y, 0);
+            const float p_nyq = (z0x - z0y) * (z0x - z0y);
+            fmax_ = fmaxf(fmax_, p_nyq);
+            if (lane == 0) { pbuf[1024] = p_nyq; gp[1024] = p_nyq; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) fmax_ = fmaxf(fmax_, __shfl_xor_sync(0xffffffffu, fmax_, o));
+        __syncwarp();
+
+        // ---- sparse slaney mel (<= 2 filters per bin) + 10 log10 ---------------------------------
+        float* gl = g_logmel + size_t(t) * kMels;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int f = lane + 32 * g;
+            const int st = sm.mel_start[f], ln = sm.mel_len[f], pt = sm.mel_ptr[f];
+            float acc = 0.f;
+            for (int j = 0; j < ln; ++j) acc = fmaf(sm.mel_w[pt + j], pbuf[st + j], acc);
+            const float L = 10.0f * log10f(fmaxf(acc, 1e-10f));
+            gl[f] = L;
+            warp_lmax = fmaxf(warp_lmax, L);
+        }
+
+        // ---- piptrack: thresholded local maxima in [150, 4000) Hz, parabolic refinement ----------
+        const float ref = 0.1f * fmax_;
+        unsigned pkmask = 0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int k = lane + 32 * q;
+            if (k >= kPipLo) {
+                const float c = pbuf[k], l = pbuf[k - 1], r = pbuf[k + 1];
+                const float qc = c > ref ? c : 0.f, ql = l > ref ? l : 0.f, qr = r > ref ? r : 0.f;
+                if (qc > ql && qc >= qr) pkmask |= 1u << q;
+            }
+        }
+        int npk = __popc(pkmask);
+        int incl = npk;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        if (total > 0) {
+            int base = 0;
+            if (lane == 31) base = atomicAdd(&sc.peak_count[li], total);
+            base = __shfl_sync(0xffffffffu, base, 31);
+            int slot = base + incl - npk;
+            while (pkmask) {
+                const int q = __ffs(pkmask) - 1;
+                pkmask &= pkmask - 1;
+                const int k = lane + 32 * q;
+                const float c = pbuf[k], l = pbuf[k - 1], r = pbuf[k + 1];
+                // librosa >= 0.10 _parabolic_interpolation evaluates in float64 and stores float32
+                const double a = double(r) + double(l) - 2.0 * double(c);
+                const double b = (double(r) - double(l)) / 2.0;
+                const float shift = (fabs(b) >= fabs(a)) ? 0.f : float(-b / a);
+                const float avg = (r - l) * 0.5f;                       // np.gradient, float32
+                const float dskew = (0.5f * avg) * shift;
+                const float pitch = float((double(k) + double(shift)) * 16000.0 / 2048.0);
+                g_peaks[slot++] = make_float2(pitch, c + dskew);
+            }
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) warp_lmax = fmaxf(warp_lmax, __shfl_xor_sync(0xffffffffu, warp_lmax, o));
+    if (lane == 0 && warp_lmax > -INFINITY) atomicMax(&sc.lmax_enc[li], enc_f32(warp_lmax));
+    if (__any_sync(0xffffffffu, nonfinite) && lane == 0) atomicOr(&status[inst], kStatusNonFinite);
+}
+
+// ------------------------------------------------------------------------------------------
+// librosa.estimate_tuning: threshold = median(mag), histogram of mod(12 log2(f / 27.5), 1)
+// folded to [-0.5, 0.5) over 100 bins, first arg-max.
+__global__ void __launch_bounds__(256)
+k_tuning(const DeviceTables tb, FeatScratch sc) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned s_prefix, s_k;
+    __shared__ unsigned s_cle, s_mingt;
+    const int li = blockIdx.x, tid = threadIdx.x;
+    const int N = min(sc.peak_count[li], sc.t_max * kMaxPeaksPerFrame);
+    const float2* pk = sc.peaks + size_t(li) * sc.t_max * kMaxPeaksPerFrame;
+    if (N == 0) {
+        if (tid == 0) sc.tuning_idx[li] = kTunings / 2;       // no pitches -> tuning 0.0
+        return;
+    }
+    // radix select of rank r0 = (N-1)/2 on the (positive) float bit patterns
+    if (tid == 0) { s_prefix = 0; s_k = unsigned(N - 1) / 2; }
+    unsigned mask = 0;
+    for (int pass = 3; pass >= 0; --pass) {
+        hist[tid] = 0;
+        __syncthreads();
+        const unsigned prefix = s_prefix;
+        for (int i = tid; i < N; i += 256) {
+            const unsigned key = __float_as_uint(pk[i].y);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned k = s_k, cum = 0;
+            int b = 0;
+            for (; b < 256; ++b) {
+                if (cum + hist[b] > k) break;
+                cum += hist[b];
+            }
+            s_k = k - cum;
+            s_prefix = prefix | (unsigned(b) << (8 * pass));
+        }
+        mask |= 0xffu << (8 * pass);
+        __syncthreads();
+    }
+    const unsigned v0 = s_prefix;
+    if (tid == 0) { s_cle = 0; s_mingt = 0xffffffffu; }
+    for (int i = tid; i < 100; i += 256) hist[i] = 0;
+    __syncthreads();
+    unsigned cle = 0, mingt = 0xffffffffu;
+    for (int i = tid; i < N; i += 256) {
+        const unsigned key = __float_as_uint(pk[i].y);
+        if (key <= v0) ++cle; else mingt = min(mingt, key);
+    }
+    atomicAdd(&s_cle, cle);
+    atomicMin(&s_mingt, mingt);
+    __syncthreads();
+    const unsigned r1 = unsigned(N) / 2;
+    const unsigned v1 = (s_cle >= r1 + 1) ? v0 : s_mingt;
+    const float thr = (__uint_as_float(v0) + __uint_as_float(v1)) * 0.5f;      // np.median: mean of the two middles
+    for (int i = tid; i < N; i += 256) {
+        const float2 p = pk[i];
+        if (p.y >= thr && p.x > 0.f) {
+            const float octs = float(log2(double(p.x / 27.5f)));               // float32 log2, correctly rounded
+            float r = fmodf(12.0f * octs, 1.0f);
+            if (r >= 0.5f) r -= 1.0f;
+            const double x = double(r);
+            int b = int(floor((x + 0.5) * 100.0));
+            b = max(0, min(99, b));
+            while (b > 0 && x < tb.tuning_edges[b]) --b;
+            while (b < 99 && x >= tb.tuning_edges[b + 1]) ++b;
+            atomicAdd(&hist[b], 1u);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        unsigned best = 0; int bi = 0;
+        for (int b = 0; b < 100; ++b) if (hist[b] > best) { best = hist[b]; bi = b; }
+        sc.tuning_idx[li] = bi;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+struct CepstraSmem {
+    float dctT[kMels * kMfcc];          // [m][k]
+    float lrow[kWarps][kMels];
+};
+
+__global__ void __launch_bounds__(kThreads)
+k_frame_cepstra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch sc) {
+    __shared__ CepstraSmem sm;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int li = blockIdx.x;
+    const InstSrc src = inst_source(cv, inst0 + li);
+    const int T = frames_of(src.n);
+    const int t_begin = blockIdx.y * kFramesPerCta;
+    if (T < 9 || t_begin >= T) return;
+    const int t_end = min(T, t_begin + kFramesPerCta);
+    for (int i = tid; i < kMels * kMfcc; i += kThreads) {
+        const int m = i / kMfcc, k = i % kMfcc;
+        sm.dctT[i] = tb.dct[k * kMels + m];
+    }
+    __syncthreads();
+    const float thr = dec_f32(sc.lmax_enc[li]) - 80.0f;                 // power_to_db top_db over the WHOLE clip
+    const float4* wtab = reinterpret_cast<const float4*>(tb.chroma + size_t(sc.tuning_idx[li]) * kBins * kChroma);
+    const float* g_power = sc.power + size_t(li) * sc.t_max * kBinsPad;
+    const float* g_logmel = sc.logmel + size_t(li) * sc.t_max * kMels;
+    float* g_mfcc = sc.mfcc + size_t(li) * sc.t_max * kMfcc;
+    float* g_chroma = sc.chroma + size_t(li) * sc.t_max * kChroma;
+    float* lrow = sm.lrow[warp];
+
+    for (int t = t_begin + warp; t < t_end; t += kWarps) {
+        // ---- clamp + DCT-II: lane k < 20 owns coefficient k --------------------------------------
+#pragma unroll
+        for (int g = 0; g < 4; ++g) lrow[lane + 32 * g] = fmaxf(g_logmel[size_t(t) * kMels + lane + 32 * g], thr);
+        __syncwarp();
+        if (lane < kMfcc) {
+            float acc = 0.f;
+#pragma unroll 8
+            for (int m = 0; m < kMels; ++m) acc = fmaf(lrow[m], sm.dctT[m * kMfcc + lane], acc);
+            g_mfcc[size_t(t) * kMfcc + lane] = acc;
+        }
+        // ---- chroma: 12 x 1025 projection, lane owns bins lane + 32 j ----------------------------
+        float acc[kChroma];
+#pragma unroll
+        for (int c = 0; c < kChroma; ++c) acc[c] = 0.f;
+        const float* gp = g_power + size_t(t) * kBinsPad;
+#pragma unroll 4
+        for (int j = 0; j < 32; ++j) {
+            const int k = lane + 32 * j;
+            const float p = gp[k];
+            const float4 w0 = __ldg(&wtab[k * 3 + 0]), w1 = __ldg(&wtab[k * 3 + 1]), w2 = __ldg(&wtab[k * 3 + 2]);
+            acc[0] = fmaf(w0.x, p, acc[0]); acc[1] = fmaf(w0.y, p, acc[1]); acc[2] = fmaf(w0.z, p, acc[2]);
+            acc[3] = fmaf(w0.w, p, acc[3]); acc[4] = fmaf(w1.x, p, acc[4]); acc[5] = fmaf(w1.y, p, acc[5]);
+            acc[6] = fmaf(w1.z, p, acc[6]); acc[7] = fmaf(w1.w, p, acc[7]); acc[8] = fmaf(w2.x, p, acc[8]);
+            acc[9] = fmaf(w2.y, p, acc[9]); acc[10] = fmaf(w2.z, p, acc[10]); acc[11] = fmaf(w2.w, p, acc[11]);
+        }
+        if (lane == 0) {
+            const int k = 1024;
+            const float p = gp[k];
+            const float4 w0 = __ldg(&wtab[k * 3 + 0]), w1 = __ldg(&wtab[k * 3 + 1]), w2 = __ldg(&wtab[k * 3 + 2]);
+            acc[0] = fmaf(w0.x, p, acc[0]); acc[1] = fmaf(w0.y, p, acc[1]); acc[2] = fmaf(w0.z, p, acc[2]);
+            acc[3] = fmaf(w0.w, p, acc[3]); acc[4] = fmaf(w1.x, p, acc[4]); acc[5] = fmaf(w1.y, p, acc[5]);
+            acc[6] = fmaf(w1.z, p, acc[6]); acc[7] = fmaf(w1.w, p, acc[7]); acc[8] = fmaf(w2.x, p, acc[8]);
+            acc[9] = fmaf(w2.y, p, acc[9]); acc[10] = fmaf(w2.z, p, acc[10]); acc[11] = fmaf(w2.w, p, acc[11]);
+        }
+        float cmax = 0.f;
+#pragma unroll
+        for (int c = 0; c < kChroma; ++c) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+            cmax = fmaxf(cmax, fabsf(acc[c]));
+        }
+        if (cmax < FLT_MIN) cmax = 1.0f;                                 // util.normalize: below tiny -> unscaled
+        float mine = 0.f;
+#pragma unroll
+        for (int c = 0; c < kChroma; ++c) if (lane == c) mine = acc[c];
+        if (lane < kChroma) g_chroma[size_t(t) * kChroma + lane] = __fdiv_rn(mine, cmax);
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_clip_stats(const ClipView cv, int inst0, FeatScratch sc, float* __restrict__ out_raw, float* __restrict__ out_clean,
+             const int32_t* __restrict__ status) {
+    constexpr int kParts = 12;
+    __shared__ double red[kParts][kMfcc][6];
+    __shared__ double cred[21][kChroma][2];
+    const int tid = threadIdx.x, li = blockIdx.x, inst = inst0 + li;
+    const bool clean = inst >= cv.n_clips;
+    const int c = clean ? inst - cv.n_clips : inst;
+    float* out = (clean ? out_clean : out_raw) + size_t(c) * kFeat;
+    const int st = status[inst];
+    if (st & (kStatusShort | kStatusNonFinite | kStatusBadLength)) {
+        for (int i = tid; i < kFeat; i += 256) out[i] = 0.f;
+        return;
+    }
+    int n = cv.lengths[c];
+    const int T = frames_of(n);
+    const float* M = sc.mfcc + size_t(li) * sc.t_max * kMfcc;
+    const float* C = sc.chroma + size_t(li) * sc.t_max * kChroma;
+    if (tid < kParts * kMfcc) {
+        const int k = tid % kMfcc, part = tid / kMfcc;
+        const double x0 = double(M[k]);               // shift by the first frame: exact zero std for constant rows
+        double s[6] = {0, 0, 0, 0, 0, 0};
+        for (int t = part; t < T; t += kParts) {
+            const int tc = min(max(t, 4), T - 5);     // savgol mode='interp' with polyorder == deriv: edges replicate
+            float w[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) w[j] = M[size_t(tc - 4 + j) * kMfcc + k];
+            const double d1 = (4.0 * (double(w[8]) - double(w[0])) + 3.0 * (double(w[7]) - double(w[1])) +
+                               2.0 * (double(w[6]) - double(w[2])) + (double(w[5]) - double(w[3]))) / 60.0;
+            const double d2 = (28.0 * (double(w[0]) + double(w[8])) + 7.0 * (double(w[1]) + double(w[7])) -
+                               8.0 * (double(w[2]) + double(w[6])) - 17.0 * (double(w[3]) + double(w[5])) -
+                               20.0 * double(w[4])) / 462.0;
+            const float d1f = float(d1), d2f = float(d2);      // librosa.feature.delta returns float32
+            const double x = double(M[size_t(t) * kMfcc + k]) - x0;
+            s[0] += x; s[1] += x * x;
+            s[2] += double(d1f); s[3] += double(d1f) * double(d1f);
+            s[4] += double(d2f); s[5] += double(d2f) * double(d2f);
+        }
+#pragma unroll
+        for (int j = 0; j < 6; ++j) red[part][k][j] = s[j];
+    }
+    if (tid < 21 * kChroma) {
+        const int ch = tid % kChroma, part = tid / kChroma;
+        double a = 0, b = 0;
+        for (int t = part; t < T; t += 21) {
+            const double x = double(C[size_t(t) * kChroma + ch]);
+            a += x; b += x * x;
+        }
+        cred[part][ch][0] = a; cred[part][ch][1] = b;
+    }
+    __syncthreads();
+    const double invT = 1.0 / double(T);
+    if (tid < kMfcc * 3) {
+        const int k = tid % kMfcc, which = tid / kMfcc;          // 0 mfcc, 1 delta, 2 delta2
+        double a = 0, b = 0;
+        for (int p = 0; p < kParts; ++p) { a += red[p][k][2 * which]; b += red[p][k][2 * which + 1]; }
+        const double mean = a * invT;
+        const double var = fmax(b * invT - mean * mean, 0.0);
+        const double shift = which == 0 ? double(M[k]) : 0.0;
+        out[which * 40 + k] = float(mean + shift);
+        out[which * 40 + 20 + k] = float(sqrt(var));
+    } else if (tid >= 64 && tid < 64 + kChroma) {
+        const int ch = tid - 64;
+        double a = 0, b = 0;
+        for (int p = 0; p < 21; ++p) { a += cred[p][ch][0]; b += cred[p][ch][1]; }
+        const double mean = a * invT;
+        const double var = fmax(b * invT - mean * mean, 0.0);
+        out[120 + ch] = float(mean);
+        out[132 + ch] = float(sqrt(var));
+    } else if (tid >= 96 && tid < 96 + (kFeat - kAudioFeat)) {
+        out[kAudioFeat + tid - 96] = 0.f;                        // extract_text_features("") -> zeros(5)
+    }
+}
+
+}  // namespace
+
+size_t feat_scratch_bytes(int n_inst, int t_max) {
+    auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+    const size_t f = size_t(n_inst) * t_max;
+    return al(f * kBinsPad * 4) + al(f * kMels * 4) + al(f * kMfcc * 4) + al(f * kChroma * 4) +
+           al(f * kMaxPeaksPerFrame * 8) + 3 * al(size_t(n_inst) * 4);
+}
+
+void feat_scratch_carve(void* base, int n_inst, int t_max, FeatScratch* out) {
+    auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+    unsigned char* p = static_cast<unsigned char*>(base);
+    const size_t f = size_t(n_inst) * t_max;
+    out->power = reinterpret_cast<float*>(p); p += al(f * kBinsPad * 4);
+    out->logmel = reinterpret_cast<float*>(p); p += al(f * kMels * 4);
+    out->mfcc = reinterpret_cast<float*>(p); p += al(f * kMfcc * 4);
+    out->chroma = reinterpret_cast<float*>(p); p += al(f * kChroma * 4);
+    out->peaks = reinterpret_cast<float2*>(p); p += al(f * kMaxPeaksPerFrame * 8);
+    out->peak_count = reinterpret_cast<int*>(p); p += al(size_t(n_inst) * 4);
+    out->lmax_enc = reinterpret_cast<int*>(p); p += al(size_t(n_inst) * 4);
+    out->tuning_idx = reinterpret_cast<int*>(p);
+    out->t_max = t_max;
+}
+
+cudaError_t launch_features(const DeviceTables& tb, const ClipView& cv, int inst0, int n_inst, const FeatScratch& sc,
+                            float* out_raw, float* out_clean, int32_t* status, cudaStream_t stream) {
+    if (n_inst <= 0) return cudaSuccess;
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(k_frame_spectra, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             int(sizeof(SpectraSmem)));
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 63] = true;
+    }
+    const int gx = (sc.t_max + kFramesPerCta - 1) / kFramesPerCta;
+    k_feat_init<<<(n_inst + 255) / 256, 256, 0, stream>>>(sc.peak_count, sc.lmax_enc, status, cv, inst0, n_inst);
+    k_frame_spectra<<<dim3(n_inst, gx), kThreads, sizeof(SpectraSmem), stream>>>(tb, cv, inst0, sc, status);
+    k_tuning<<<n_inst, 256, 0, stream>>>(tb, sc);
+    k_frame_cepstra<<<dim3(n_inst, gx), kThreads, 0, stream>>>(tb, cv, inst0, sc);
+    k_clip_stats<<<n_inst, 256, 0, stream>>>(cv, inst0, sc, out_raw, out_clean, status);
+    return cudaGetLastError();
+}
+
+}  // namespace dys

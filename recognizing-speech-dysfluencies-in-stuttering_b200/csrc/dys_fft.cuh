@@ -1,0 +1,197 @@
+// Warp-resident FFTs for the dysfluency front-end (sm_100a).
+//
+// One warp transforms one STFT frame.  A length-N complex FFT (N = 32*R, R = 32 for the
+// 2048-sample feature frames in fp32, R = 16 for the 1024-sample spectral-gate frames in
+// fp64) is split as  j = lane + 32*m,  k = kA + R*kB :
+//     pass 1: R-point FFT over m in registers (each lane owns one residue class),
+//     twiddle W_N^(lane*kA), one transposition through a padded shared-memory tile,
+//     pass 2: 32-point FFT over the lanes' residue, again entirely in registers.
+// The transform leaves  v[q] = Z[lane + 32*q]  -- the same "stride-32" ownership the input
+// had -- so real-FFT split, masking and the inverse transform chain without re-layout, and
+// every shared-memory access in the exchange is conflict-free (row pad 33).
+//
+// Replaces: numpy.fft.rfft as called by librosa.stft inside librosa.feature.mfcc /
+// chroma_stft (reference pipeline1.py:216,227) and by noisereduce (pipeline1.py:140).
+#pragma once
+#include <cuda_runtime.h>
+#include <type_traits>
+#include <utility>
+
+namespace dys {
+
+template <typename T> struct cx_of;
+template <> struct cx_of<float>  { using type = float2; };
+template <> struct cx_of<double> { using type = double2; };
+template <typename T> using cx = typename cx_of<T>::type;
+
+template <typename T> __device__ __forceinline__ cx<T> mk(T x, T y) { cx<T> r; r.x = x; r.y = y; return r; }
+template <typename C> __device__ __forceinline__ C cadd(C a, C b) { a.x += b.x; a.y += b.y; return a; }
+template <typename C> __device__ __forceinline__ C csub(C a, C b) { a.x -= b.x; a.y -= b.y; return a; }
+template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
+    C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
+}
+
+// ---- compile-time loops -------------------------------------------------------------------
+template <typename F, int... I>
+__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) {
+    (f(std::integral_constant<int, I>{}), ...);
+}
+template <int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+    static_for_impl(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
+}
+
+// ---- constant twiddles: cos(2*pi*i/64), i = 0..16 -----------------------------------------
+__host__ __device__ constexpr double kCosQ64(int i) {
+    constexpr double t[17] = {
+        1.0, 0.995184726672196886245, 0.980785280403230449126, 0.956940335732208864936,
+        0.923879532511286756128, 0.881921264348355029713, 0.831469612302545237079,
+        0.773010453362736960811, 0.707106781186547524401, 0.634393284163645498215,
+        0.555570233019602224743, 0.471396736825997648556, 0.382683432365089771728,
+        0.290284677254462367636, 0.195090322016128267848, 0.0980171403295606019942, 0.0};
+    return t[i];
+}
+// cos / sin of 2*pi*i/64 for 0 <= i <= 32
+__host__ __device__ constexpr double kCos64(int i) { return i <= 16 ? kCosQ64(i) : -kCosQ64(32 - i); }
+__host__ __device__ constexpr double kSin64(int i) { return i <= 16 ? kCosQ64(16 - i) : kCosQ64(i - 16); }
+
+__host__ __device__ constexpr int bitrev(int x, int bits) {
+    int r = 0;
+    for (int b = 0; b < bits; ++b) r |= ((x >> b) & 1) << (bits - 1 - b);
+    return r;
+}
+__host__ __device__ constexpr int ilog2(int n) { int b = 0; while ((1 << b) < n) ++b; return b; }
+
+// d * W_N^I  with  W_N = exp(-2*pi*i/N),  0 <= I < N/2,  N in {2,...,64}
+template <int I, int N, typename T>
+__device__ __forceinline__ cx<T> mul_w(cx<T> d) {
+    if constexpr (I == 0) {
+        return d;
+    } else if constexpr (4 * I == N) {                 // -i
+        return mk<T>(d.y, -d.x);
+    } else if constexpr (8 * I == N) {                 // (1 - i)/sqrt2
+        constexpr T c = T(0.707106781186547524401);
+        return mk<T>((d.x + d.y) * c, (d.y - d.x) * c);
+    } else if constexpr (8 * I == 3 * N) {             // (-1 - i)/sqrt2
+        constexpr T c = T(0.707106781186547524401);
+        return mk<T>((d.y - d.x) * c, -(d.x + d.y) * c);
+    } else {
+        constexpr T c = T(kCos64(I * (64 / N)));
+        constexpr T s = T(kSin64(I * (64 / N)));
+        return mk<T>(d.x * c + d.y * s, d.y * c - d.x * s);
+    }
+}
+
+// In-register radix-2 decimation-in-frequency FFT.  Output is bit-reversed:
+// X[k] ends in v[bitrev(k, log2 N)].
+template <int N, int LEN, typename T>
+__device__ __forceinline__ void dif_stage(cx<T> (&v)[N]) {
+    static_for<N / LEN>([&](auto ib) {
+        constexpr int base = decltype(ib)::value * LEN;
+        static_for<LEN / 2>([&](auto ii) {
+            constexpr int i = decltype(ii)::value;
+            const cx<T> a = v[base + i];
+            const cx<T> b = v[base + i + LEN / 2];
+            v[base + i] = cadd(a, b);
+            v[base + i + LEN / 2] = mul_w<i, LEN, T>(csub(a, b));
+        });
+    });
+    if constexpr (LEN > 2) dif_stage<N, LEN / 2, T>(v);
+}
+template <int N, typename T>
+__device__ __forceinline__ void fft_reg(cx<T> (&v)[N]) { dif_stage<N, N, T>(v); }
+
+// Shared-memory footprints (in complex elements) of the exchange tiles.
+constexpr int kXbuf1024 = 32 * 33;   // float2  ->  8448 B
+constexpr int kXbuf512 = 16 * 33;    // double2 ->  8448 B
+
+// ---- 1024-point complex FFT, fp32, one warp ------------------------------------------------
+// in : v[m] = z[lane + 32 m]          out: v[q] = Z[lane + 32 q]
+// xbuf: 32x33 float2 private to the warp; tw[kA*32 + l] = W_1024^(l*kA)
+__device__ __forceinline__ void warp_fft1024(float2 (&v)[32], float2* xbuf, const float2* __restrict__ tw, int lane) {
+    fft_reg<32, float>(v);
+    static_for<32>([&](auto ik) {
+        constexpr int kA = decltype(ik)::value;
+        constexpr int r = bitrev(kA, 5);
+        float2 val = v[r];
+        if constexpr (kA != 0) val = cmul(val, tw[kA * 32 + lane]);
+        xbuf[lane * 33 + kA] = val;
+    });
+    __syncwarp();
+    static_for<32>([&](auto il) {
+        constexpr int l = decltype(il)::value;
+        v[l] = xbuf[l * 33 + lane];
+    });
+    __syncwarp();
+    fft_reg<32, float>(v);
+    float2 o[32];
+    static_for<32>([&](auto iq) {
+        constexpr int q = decltype(iq)::value;
+        o[q] = v[bitrev(q, 5)];
+    });
+    static_for<32>([&](auto iq) { constexpr int q = decltype(iq)::value; v[q] = o[q]; });
+}
+
+// ---- 512-point complex FFT, fp64, one warp -------------------------------------------------
+// in : v[m] = z[lane + 32 m], m < 16   out: v[q] = Z[lane + 32 q], q < 16
+// xbuf: 16x33 double2 private to the warp; tw512[kA*32 + l] = W_512^(l*kA);
+// tw32h[h*16 + l'] = (h ? W_32^l' : 1)
+__device__ __forceinline__ void warp_fft512(double2 (&v)[16], double2* xbuf, const double2* __restrict__ tw512,
+                                            const double2* __restrict__ tw32h, int lane) {
+    fft_reg<16, double>(v);
+    static_for<16>([&](auto ik) {
+        constexpr int kA = decltype(ik)::value;
+        constexpr int r = bitrev(kA, 4);
+        double2 val = v[r];
+        if constexpr (kA != 0) val = cmul(val, tw512[kA * 32 + lane]);
+        xbuf[kA * 33 + lane] = val;
+    });
+    __syncwarp();
+    const int kA = lane & 15, h = lane >> 4;
+    const double sgn = h ? -1.0 : 1.0;
+    static_for<16>([&](auto il) {
+        constexpr int l = decltype(il)::value;
+        const double2 a = xbuf[kA * 33 + l];
+        const double2 b = xbuf[kA * 33 + l + 16];
+        double2 d = mk<double>(a.x + sgn * b.x, a.y + sgn * b.y);
+        if constexpr (l != 0) d = cmul(d, tw32h[h * 16 + l]);
+        v[l] = d;
+    });
+    __syncwarp();
+    fft_reg<16, double>(v);
+    double2 o[16];
+    static_for<16>([&](auto iq) {
+        constexpr int q = decltype(iq)::value;
+        o[q] = v[bitrev(q, 4)];
+    });
+    static_for<16>([&](auto iq) { constexpr int q = decltype(iq)::value; v[q] = o[q]; });
+}
+
+// Partner fetch for the real-FFT split: lane holding k = lane + 32 q needs Z[NH - k], which
+// lives in lane (32 - lane) & 31 at register Q-1-q (lane 0: its own register (Q - q) % Q).
+template <int Q>
+__device__ __forceinline__ void partner_f(const float2 (&v)[Q], float2 (&p)[Q], int lane) {
+    const int src = (32 - lane) & 31;
+    static_for<Q>([&](auto iq) {
+        constexpr int q = decltype(iq)::value;
+        float2 s;
+        s.x = __shfl_sync(0xffffffffu, v[Q - 1 - q].x, src);
+        s.y = __shfl_sync(0xffffffffu, v[Q - 1 - q].y, src);
+        if (lane == 0) s = v[(Q - q) % Q];
+        p[q] = s;
+    });
+}
+template <int Q>
+__device__ __forceinline__ void partner_d(const double2 (&v)[Q], double2 (&p)[Q], int lane) {
+    const int src = (32 - lane) & 31;
+    static_for<Q>([&](auto iq) {
+        constexpr int q = decltype(iq)::value;
+        double2 s;
+        s.x = __shfl_sync(0xffffffffu, v[Q - 1 - q].x, src);
+        s.y = __shfl_sync(0xffffffffu, v[Q - 1 - q].y, src);
+        if (lane == 0) s = v[(Q - q) % Q];
+        p[q] = s;
+    });
+}
+
+}  // namespace dys

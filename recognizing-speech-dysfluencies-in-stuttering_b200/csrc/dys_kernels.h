@@ -1,0 +1,84 @@
+// Internal launch interface between the C-ABI (dys_api.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+
+#include "dys_tables.h"
+
+namespace dys {
+
+// status bits written per clip instance (mirrors the reference's "log + zeros / None" conventions)
+constexpr int kStatusShort = 1;       // T < 9 frames: librosa.feature.delta raises -> zeros(144)   (pipeline1.py:237-239)
+constexpr int kStatusNonFinite = 2;   // librosa.util.valid_audio raises -> zeros(144)
+constexpr int kStatusCleanFallback = 4;  // denoise/normalise failed -> raw clip used as "clean"     (pipeline1.py:385-387)
+constexpr int kStatusBadLength = 8;   // length < 0 or > max_len passed by the caller
+
+__host__ __device__ inline int frames_of(int n) { return 1 + n / kHop; }
+
+// One "instance" = one clip on one branch (raw or clean).  Instances [0, n_clips) are the raw
+// branch, [n_clips, 2 n_clips) the clean branch of clip (i - n_clips).
+struct ClipView {
+    const float* audio;          // raw samples (packed buffer)
+    const int64_t* starts;       // [n_clips] first sample of clip c in `audio`
+    const int32_t* lengths;      // [n_clips]
+    int n_clips;
+    int max_len;                 // caller-supplied upper bound on lengths
+    // clean branch (null when raw only)
+    const float* clean;          // [n_clips][clean_pitch] denoised float32, before normalise/quantise
+    int64_t clean_pitch;
+    const float* clean_peak;     // [n_clips] max |clean|
+    const int32_t* clean_flag;   // [n_clips] non-zero -> fall back to the raw samples
+};
+
+// Scratch of one feature sub-batch (all device pointers, sized for n_inst x t_max frames).
+struct FeatScratch {
+    float* power;        // [n_inst][t_max][kBinsPad]
+    float* logmel;       // [n_inst][t_max][kMels]
+    float* mfcc;         // [n_inst][t_max][kMfcc]
+    float* chroma;       // [n_inst][t_max][kChroma]
+    float2* peaks;       // [n_inst][t_max * kMaxPeaksPerFrame]  (pitch, mag)
+    int* peak_count;     // [n_inst]
+    int* lmax_enc;       // [n_inst] order-preserving int encoding of max log-mel
+    int* tuning_idx;     // [n_inst]
+    int t_max;
+};
+size_t feat_scratch_bytes(int n_inst, int t_max);
+void feat_scratch_carve(void* base, int n_inst, int t_max, FeatScratch* out);
+
+// Runs the feature pipeline for instances [inst0, inst0 + n_inst) and writes out[(inst) * 149].
+// out_raw / out_clean: [n_clips][149]; status: [2 * n_clips] (or [n_clips] when raw only).
+cudaError_t launch_features(const DeviceTables& tb, const ClipView& cv, int inst0, int n_inst, const FeatScratch& sc,
+                            float* out_raw, float* out_clean, int32_t* status, cudaStream_t stream);
+
+// Spectral-gate scratch for a sub-batch of chunks.
+struct NrScratch {
+    double* mag;       // [n_items][ta_max][kNrBinsPad]   |STFT| then raw sigmoid mask (in place)
+    double* fwd;       // [n_items][ta_max][kNrBinsPad]   forward IIR state, then the smoothed mask
+    double* frames;    // [n_items][ta_max][kNrFft]       windowed inverse frames
+    int ta_max;
+};
+size_t nr_scratch_bytes(int n_items, int ta_max);
+void nr_scratch_carve(void* base, int n_items, int ta_max, NrScratch* out);
+int nr_ta_max(int max_len);            // active-frame bound for one chunk
+int nr_chunks_of(int max_len);         // chunks per clip bound (1 unless max_len > 600000)
+
+// Denoise items [item0, item0 + n_items) (item = clip * chunks_per_clip + chunk): writes
+// clean[clip][...] (float32, pre-normalise), atomically maxes clean_peak[clip] and ORs clean_flag[clip].
+cudaError_t launch_denoise(const DeviceTables& tb, const ClipView& cv, float* clean, float* clean_peak, int32_t* clean_flag,
+                           int chunks_per_clip, int item0, int n_items, const NrScratch& sc, float prop_decrease,
+                           cudaStream_t stream);
+cudaError_t launch_clean_init(const ClipView& cv, float* clean_peak, int32_t* clean_flag, cudaStream_t stream);
+cudaError_t launch_quantize_pcm(const ClipView& cv, int16_t* pcm, const int64_t* pcm_starts, cudaStream_t stream);
+
+// CMVN: acc[0] = n, acc[1..149] = sum (x - shift), acc[150..298] = sum (x - shift)^2
+// (float64, fixed summation order -> bit-reproducible); shift may be null (= 0).
+constexpr int kCmvnPartials = 128;
+constexpr int kCmvnAcc = 1 + 2 * kFeat;
+cudaError_t launch_cmvn_accumulate(const float* feats, int64_t n_rows, const double* shift, double* acc, double* partials,
+                                   cudaStream_t stream);
+cudaError_t launch_cmvn_finalize(const double* acc, const double* shift, double* mean, double* scale, cudaStream_t stream);
+cudaError_t launch_cmvn_apply(const float* feats, int64_t n_rows, const double* mean, const double* scale, float* out,
+                              cudaStream_t stream);
+
+}  // namespace dys

@@ -1,0 +1,471 @@
+"""Host-side mirror of the reference's feature interface, backed by libdysb200.so.
+
+Same names, argument meaning and error behaviour as the reference's functions on this path
+(/root/reference/pipeline1.py; second copy in main1.py):
+
+    load_audio                 pipeline1.py:100-106
+    clean_audio_and_cache      pipeline1.py:126-146
+    extract_audio_features     pipeline1.py:206-239
+    extract_text_features      pipeline1.py:242-254
+    extract_features           pipeline1.py:257-265
+    cached_extract_features    pipeline1.py:429-440   (a closure there; module-level here)
+
+plus the batched entry points the reference lacks (``extract_features_batch``,
+``extract_features_host``, ``build_feature_cache``).  PyTorch is only plumbing here: device
+memory, streams, pinned host buffers.  All arithmetic runs in the CUDA library through its C
+ABI; there is no CPU fallback -- without the built library or a CUDA device calls raise.
+"""
+from __future__ import annotations
+
+import logging
+import os
+import re
+from collections import Counter
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, wavio
+from ._lib import (AUDIO_FEATURE_LEN, FEATURE_LEN, SAMPLE_RATE, STATUS_BAD_LENGTH, STATUS_CLEAN_FALLBACK,
+                   STATUS_NONFINITE, STATUS_SHORT, DysError)
+
+# same module-level knobs as the reference (pipeline1.py:29-32, 77-86)
+CACHE_DIR = "cache_features"
+CLEAR_DIR = "clear_audio"
+TARGET_SR = SAMPLE_RATE
+MFCC_N = 20
+TEXT_FEATURE_LEN = 5
+TOTAL_FEATURE_LEN = FEATURE_LEN
+PROP_DECREASE = 1.0          # pipeline1.py:140 default; main1.py:605 / main.py:657 use 0.8
+
+_log = logging.getLogger(__name__)
+
+
+# ------------------------------------------------------------------------------------------
+# device plumbing
+# ------------------------------------------------------------------------------------------
+def _device(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise DysError("no CUDA device visible: the dysfluency front-end has no CPU path")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise DysError(f"device must be a CUDA device, got {device}")
+    return torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
+
+
+class _Arena:
+    """Grow-only uint8 scratch tensor per (device, slot); slots let two streams work concurrently."""
+
+    def __init__(self):
+        self._bufs: dict = {}
+
+    def get(self, device: torch.device, nbytes: int, slot: int = 0) -> torch.Tensor:
+        key = (device.index, slot)
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            self._bufs[key] = None
+            buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+            self._bufs[key] = buf
+        return buf
+
+    def clear(self):
+        self._bufs.clear()
+
+
+_arena = _Arena()
+
+
+def release_workspaces():
+    """Frees the cached device scratch."""
+    _arena.clear()
+
+
+def _run_device(d_audio: torch.Tensor, d_starts: torch.Tensor, d_lengths: torch.Tensor, max_len: int, denoise: bool,
+                prop_decrease: float, want_pcm: bool, d_pcm_starts: torch.Tensor | None, total_pcm: int, slot: int = 0,
+                workspace_bytes: int | None = None):
+    """One C-ABI call on the current stream. Returns (raw, clean | None, status, pcm | None) device tensors."""
+    lib = _lib.load()
+    dev = d_audio.device
+    n = int(d_starts.numel())
+    with torch.cuda.device(dev):
+        _lib.check(lib.dys_init(), "dys_init")
+        need = lib.dys_workspace_bytes(n, max_len, 1 if denoise else 0) if workspace_bytes is None else workspace_bytes
+        ws = _arena.get(dev, max(int(need), 256), slot)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        raw = torch.empty((n, FEATURE_LEN), dtype=torch.float32, device=dev)
+        if not denoise:
+            status = torch.empty((n,), dtype=torch.int32, device=dev)
+            _lib.check(lib.dys_features_raw(d_audio.data_ptr(), d_starts.data_ptr(), d_lengths.data_ptr(), n, max_len,
+                                            raw.data_ptr(), status.data_ptr(), ws.data_ptr(), int(need), stream),
+                       "dys_features_raw")
+            return raw, None, status, None
+        clean = torch.empty((n, FEATURE_LEN), dtype=torch.float32, device=dev)
+        status = torch.empty((2 * n,), dtype=torch.int32, device=dev)
+        pcm = torch.empty((total_pcm,), dtype=torch.int16, device=dev) if want_pcm else None
+        _lib.check(lib.dys_features_raw_clean(d_audio.data_ptr(), d_starts.data_ptr(), d_lengths.data_ptr(), n, max_len,
+                                              float(prop_decrease), raw.data_ptr(), clean.data_ptr(), status.data_ptr(),
+                                              pcm.data_ptr() if want_pcm else None,
+                                              d_pcm_starts.data_ptr() if want_pcm else None, ws.data_ptr(), int(need), stream),
+                   "dys_features_raw_clean")
+        return raw, clean, status, pcm
+
+
+def _pack_host(clips: Sequence) -> tuple[torch.Tensor, np.ndarray, np.ndarray, int]:
+    """Packs variable-length host clips into one pinned float32 buffer; clip starts are 4-sample aligned."""
+    lens = np.asarray([0 if c is None else int(np.asarray(c).shape[0]) for c in clips], dtype=np.int64)
+    padded = (lens + 3) & ~3
+    starts = np.zeros(len(clips), dtype=np.int64)
+    if len(clips) > 1:
+        starts[1:] = np.cumsum(padded)[:-1]
+    total = int(padded.sum()) if len(clips) else 0
+    buf = torch.zeros(max(total, 4), dtype=torch.float32).pin_memory()
+    view = buf.numpy()
+    for c, s, n in zip(clips, starts, lens):
+        if n:
+            view[s:s + n] = np.asarray(c, dtype=np.float32).reshape(-1)
+    return buf, starts, lens.astype(np.int32), int(lens.max()) if len(clips) else 0
+
+
+# ------------------------------------------------------------------------------------------
+# batched entry points
+# ------------------------------------------------------------------------------------------
+def extract_features_batch(audio, lengths=None, starts=None, sr: int = TARGET_SR, denoise: bool = False,
+                           prop_decrease: float | None = None, return_status: bool = False, return_pcm: bool = False,
+                           device=None):
+    """149-dim feature vectors for a batch of 16 kHz clips (row i == reference ``extract_features(clip_i, sr)``).
+
+    audio   * list of 1-D float arrays (numpy / CPU torch), variable length, or
+            * 2-D [B, n] numpy / torch tensor (CPU or CUDA) of equal-length clips, or
+            * 1-D CUDA/CPU tensor of packed samples with ``starts`` (int64[B]) and ``lengths`` (int32[B]);
+              windows may overlap (long-form sliding windows need no copy).
+    denoise False -> raw[B,149];  True -> (raw[B,149], clean[B,149]) where clean goes through the
+            reference's spectral gate, peak normalisation and PCM-16 round trip.
+    Returns CUDA float32 tensors (plus int32 status [B] or [2B], plus a list of int16 PCM tensors).
+    """
+    if sr != TARGET_SR:
+        raise ValueError(f"only sr={TARGET_SR} is supported (the reference always resamples to TARGET_SR)")
+    prop = PROP_DECREASE if prop_decrease is None else float(prop_decrease)
+    dev = _device(device if device is not None else (audio.device if isinstance(audio, torch.Tensor) and audio.is_cuda else None))
+    with torch.cuda.device(dev):
+        if isinstance(audio, (list, tuple)):
+            host, h_starts, h_lens, max_len = _pack_host(audio)
+            d_audio = host.to(dev, non_blocking=True)
+        else:
+            t = audio if isinstance(audio, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32))
+            if t.dtype != torch.float32:
+                t = t.float()
+            if t.dim() == 2:
+                B, n = t.shape
+                t = t.contiguous()
+                h_starts = np.arange(B, dtype=np.int64) * n
+                h_lens = np.full(B, n, dtype=np.int32) if lengths is None else np.asarray(lengths, dtype=np.int32)
+                max_len = n
+                d_audio = t.reshape(-1).to(dev, non_blocking=True)
+            elif t.dim() == 1 and starts is not None and lengths is not None:
+                h_starts = np.asarray(starts.cpu() if isinstance(starts, torch.Tensor) else starts, dtype=np.int64)
+                h_lens = np.asarray(lengths.cpu() if isinstance(lengths, torch.Tensor) else lengths, dtype=np.int32)
+                if len(h_starts) and (h_starts.min() < 0 or int((h_starts + h_lens).max()) > t.numel()):
+                    raise ValueError("starts/lengths reach outside the sample buffer")
+                max_len = int(h_lens.max()) if len(h_lens) else 0
+                d_audio = t.contiguous().to(dev, non_blocking=True)
+            else:
+                raise ValueError("audio must be a list of clips, a [B, n] array, or packed samples with starts+lengths")
+        B = len(h_starts)
+        if B == 0:
+            empty = torch.zeros((0, FEATURE_LEN), dtype=torch.float32, device=dev)
+            res = (empty, empty.clone()) if denoise else empty
+            return res
+        d_starts = torch.from_numpy(h_starts).to(dev, non_blocking=True)
+        d_lens = torch.from_numpy(np.ascontiguousarray(h_lens)).to(dev, non_blocking=True)
+        pcm_starts = None
+        total_pcm = 0
+        if denoise and return_pcm:
+            pl = np.maximum(h_lens.astype(np.int64), 0)
+            hp = np.zeros(B, dtype=np.int64)
+            hp[1:] = np.cumsum(pl)[:-1]
+            total_pcm = int(pl.sum())
+            pcm_starts = torch.from_numpy(hp).to(dev, non_blocking=True)
+        raw, clean, status, pcm = _run_device(d_audio, d_starts, d_lens, max_len, denoise, prop, bool(denoise and return_pcm),
+                                              pcm_starts, max(total_pcm, 1))
+        # keep inputs alive until the stream has consumed them
+        for tns in (d_audio, d_starts, d_lens, pcm_starts):
+            if tns is not None:
+                tns.record_stream(torch.cuda.current_stream(dev))
+        out = [raw, clean] if denoise else [raw]
+        if return_status:
+            out.append(status)
+        if denoise and return_pcm:
+            hp_list = hp.tolist()
+            out.append([pcm[s:s + int(n)] for s, n in zip(hp_list, np.maximum(h_lens, 0))])
+        return out[0] if len(out) == 1 else tuple(out)
+
+
+def extract_features_host(audio: torch.Tensor, denoise: bool = True, prop_decrease: float | None = None,
+                          chunk_clips: int = 2048, out_raw: torch.Tensor | None = None,
+                          out_clean: torch.Tensor | None = None, device=None):
+    """End-to-end host path: equal-length clips [B, n] in (preferably pinned) HOST memory ->
+    host float32 [B,149] raw (and clean).  Clips stream to the device in chunks on two CUDA streams
+    so the PCIe copies overlap the kernels; results are copied back into pinned host tensors."""
+    if audio.is_cuda or audio.dim() != 2 or audio.dtype != torch.float32:
+        raise ValueError("audio must be a 2-D float32 CPU tensor [B, n]")
+    prop = PROP_DECREASE if prop_decrease is None else float(prop_decrease)
+    dev = _device(device)
+    B, n = audio.shape
+    if out_raw is None:
+        out_raw = torch.empty((B, FEATURE_LEN), dtype=torch.float32).pin_memory()
+    if denoise and out_clean is None:
+        out_clean = torch.empty((B, FEATURE_LEN), dtype=torch.float32).pin_memory()
+    chunk = max(1, min(int(chunk_clips), B))
+    with torch.cuda.device(dev):
+        cur = torch.cuda.current_stream(dev)
+        streams = _host_streams(dev)
+        staging = [_arena.get(dev, chunk * n * 4, slot=10 + i).view(torch.float32)[:chunk * n] for i in range(2)]
+        base_starts = (torch.arange(chunk, dtype=torch.int64) * n).to(dev)
+        base_lens = torch.full((chunk,), n, dtype=torch.int32, device=dev)
+        for s in streams:
+            s.wait_stream(cur)
+        for ci, c0 in enumerate(range(0, B, chunk)):
+            cnt = min(chunk, B - c0)
+            s = streams[ci & 1]
+            with torch.cuda.stream(s):
+                d_in = staging[ci & 1][:cnt * n]
+                d_in.copy_(audio[c0:c0 + cnt].reshape(-1), non_blocking=True)
+                raw, clean, _, _ = _run_device(d_in, base_starts[:cnt], base_lens[:cnt], n, denoise, prop, False, None, 1,
+                                               slot=1 + (ci & 1))
+                out_raw[c0:c0 + cnt].copy_(raw, non_blocking=True)
+                if denoise:
+                    out_clean[c0:c0 + cnt].copy_(clean, non_blocking=True)
+                raw.record_stream(s)
+                if clean is not None:
+                    clean.record_stream(s)
+        for s in streams:
+            cur.wait_stream(s)
+        cur.synchronize()
+    return (out_raw, out_clean) if denoise else out_raw
+
+
+_streams: dict = {}
+
+
+def _host_streams(dev: torch.device):
+    key = dev.index
+    if key not in _streams:
+        _streams[key] = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
+    return _streams[key]
+
+
+# ------------------------------------------------------------------------------------------
+# the reference's single-clip interface
+# ------------------------------------------------------------------------------------------
+def load_audio(path: str, sr: int = TARGET_SR):
+    """pipeline1.py:100-106.  Returns (float32[n], sr) or (None, None) after logging.  Only 16 kHz mono
+    PCM-16 WAV is decoded here (decode/resample of other formats is upstream of this package)."""
+    try:
+        y, s = wavio.read_wav(path)
+        if s != sr:
+            raise ValueError(f"sample rate {s} != {sr}: resampling is upstream of this package")
+        return y, s
+    except Exception as e:  # noqa: BLE001 - mirrors the reference's blanket handler
+        logging.error(f"load_audio fail {path}: {e}")
+        return None, None
+
+
+def repetition_stats_from_text(text: str):
+    """pipeline1.py:191-201."""
+    if not text:
+        return {"repetition_count": 0, "repetition_ratio": 0.0, "unique_ratio": 0.0}
+    words = re.findall(r"\b\w+\b", text.lower())
+    if len(words) < 1:
+        return {"repetition_count": 0, "repetition_ratio": 0.0, "unique_ratio": 0.0}
+    counts = Counter(words)
+    repeats = sum(c - 1 for c in counts.values() if c > 1)
+    return {"repetition_count": float(repeats), "repetition_ratio": float(repeats / len(words)),
+            "unique_ratio": float(len(set(words)) / len(words))}
+
+
+def extract_text_features(text: str) -> np.ndarray:
+    """pipeline1.py:242-254 (host-side; the reference always passes "" -> zeros(5))."""
+    if not text:
+        return np.zeros(TEXT_FEATURE_LEN, dtype=np.float32)
+    rep = repetition_stats_from_text(text)
+    words = re.findall(r"\b\w+\b", text.lower())
+    return np.array([float(len(text)), float(len(words)), rep["repetition_count"], rep["repetition_ratio"],
+                     rep["unique_ratio"]], dtype=np.float32)
+
+
+def extract_audio_features(y, sr: int = TARGET_SR) -> np.ndarray:
+    """pipeline1.py:206-239 -> float32[144]; ``None`` and every failure mode of the reference's
+    try-block (fewer than 9 frames, non-finite samples, empty input) give zeros."""
+    if y is None:
+        return np.zeros(AUDIO_FEATURE_LEN, dtype=np.float32)
+    try:
+        y = np.asarray(y, dtype=np.float32).reshape(-1)
+        if y.size == 0:
+            raise ValueError("empty clip")
+        feats = extract_features_batch([y], sr=sr)
+        return feats[0, :AUDIO_FEATURE_LEN].cpu().numpy()
+    except DysError:
+        raise                                   # a missing GPU/library is not a data error: fail loudly
+    except Exception as e:  # noqa: BLE001
+        logging.error(f"extract_audio_features error: {e}")
+        return np.zeros(AUDIO_FEATURE_LEN, dtype=np.float32)
+
+
+def extract_features(y, sr: int = TARGET_SR, transcript: str = "") -> np.ndarray:
+    """pipeline1.py:257-265 -> float32[149]."""
+    feats = np.hstack([extract_audio_features(y, sr), extract_text_features(transcript)]).astype(np.float32)
+    if feats.size != TOTAL_FEATURE_LEN:
+        out = np.zeros(TOTAL_FEATURE_LEN, dtype=np.float32)
+        out[:min(feats.size, TOTAL_FEATURE_LEN)] = feats[:TOTAL_FEATURE_LEN]
+        return out
+    return feats
+
+
+def clean_audio(y, prop_decrease: float | None = None):
+    """In-memory body of clean_audio_and_cache (pipeline1.py:140-142): int16 PCM as the reference
+    writes it, or ``None`` where the reference's except-branch fires (NaN from an all-zero clip, ...)."""
+    if y is None:
+        return None
+    y = np.asarray(y, dtype=np.float32).reshape(-1)
+    if y.size == 0:
+        return None
+    _, _, status, pcm = extract_features_batch([y], denoise=True, prop_decrease=prop_decrease, return_status=True,
+                                               return_pcm=True)
+    if int(status[1].item()) & STATUS_CLEAN_FALLBACK:
+        return None
+    return pcm[0].cpu().numpy()
+
+
+def clean_audio_and_cache(in_path: str):
+    """pipeline1.py:126-146: writes CLEAR_DIR/<stem>.wav (PCM-16) and returns its path; an existing
+    file is reused; any failure is logged and gives ``None``."""
+    base = os.path.basename(in_path).rsplit(".", 1)[0]
+    out_path = os.path.normpath(os.path.join(CLEAR_DIR, f"{base}.wav"))
+    if os.path.exists(out_path):
+        return out_path
+    y, sr = load_audio(in_path, sr=TARGET_SR)
+    if y is None:
+        return None
+    try:
+        pcm = clean_audio(y)
+        if pcm is None:
+            raise ValueError("Input must be finite")      # librosa.util.normalize's complaint
+        os.makedirs(CLEAR_DIR, exist_ok=True)
+        wavio.write_wav_pcm16(out_path, pcm, sr)
+        return out_path
+    except DysError:
+        raise
+    except Exception as e:  # noqa: BLE001
+        logging.error(f"clean_audio fail {in_path}: {e}")
+        return None
+
+
+def cached_extract_features(path: str, transcript: str, suffix: str) -> np.ndarray:
+    """pipeline1.py:429-440: cache key is CACHE_DIR/<basename-stem>_<suffix>_feats.npy."""
+    base = os.path.basename(path).rsplit(".", 1)[0]
+    cache_file = os.path.normpath(os.path.join(CACHE_DIR, f"{base}_{suffix}_feats.npy"))
+    try:
+        return np.array(np.load(cache_file, allow_pickle=True))
+    except Exception:  # noqa: BLE001
+        pass
+    y, sr = load_audio(path, sr=TARGET_SR)
+    feats = extract_features(y, sr if sr is not None else TARGET_SR, transcript)
+    os.makedirs(CACHE_DIR, exist_ok=True)
+    np.save(cache_file, feats)
+    return feats
+
+
+def build_feature_cache(paths: Sequence[str], overwrite: bool = False):
+    """Batched replacement for the reference's two per-file loops (pipeline1.py:371-417 and :447-453):
+    loads every readable clip, runs ONE raw+clean batch on the GPU and writes the same artefacts the
+    reference writes -- CLEAR_DIR/<stem>.wav, CACHE_DIR/<stem>_raw_feats.npy, CACHE_DIR/<stem>_clean_feats.npy
+    (byte-identical .npy headers: np.save of float32 (149,)).  Returns (X_before, X_after, kept_paths)."""
+    clips, kept = [], []
+    for p in paths:
+        y, _ = load_audio(p, sr=TARGET_SR)
+        if y is None:
+            continue                                              # reference: skipped += 1
+        clips.append(y)
+        kept.append(p)
+    if not clips:
+        return np.empty((0, FEATURE_LEN), np.float32), np.empty((0, FEATURE_LEN), np.float32), []
+    raw, clean, status, pcm = extract_features_batch(clips, denoise=True, return_status=True, return_pcm=True)
+    raw, clean, status = raw.cpu().numpy(), clean.cpu().numpy(), status.cpu().numpy()
+    os.makedirs(CLEAR_DIR, exist_ok=True)
+    os.makedirs(CACHE_DIR, exist_ok=True)
+    n = len(kept)
+    for i, p in enumerate(kept):
+        base = os.path.basename(p).rsplit(".", 1)[0]
+        wav = os.path.normpath(os.path.join(CLEAR_DIR, f"{base}.wav"))
+        if status[n + i] & STATUS_CLEAN_FALLBACK:
+            logging.error(f"clean_audio fail {p}: Input must be finite")
+        elif overwrite or not os.path.exists(wav):
+            wavio.write_wav_pcm16(wav, pcm[i].cpu().numpy(), TARGET_SR)
+        for suffix, row in (("raw", raw[i]), ("clean", clean[i])):
+            f = os.path.normpath(os.path.join(CACHE_DIR, f"{base}_{suffix}_feats.npy"))
+            if overwrite or not os.path.exists(f):
+                np.save(f, row)
+    return raw, clean, kept
+
+
+# ------------------------------------------------------------------------------------------
+# introspection (parity tests)
+# ------------------------------------------------------------------------------------------
+def debug_feature_stages(y, device=None) -> dict:
+    """Stage-wise intermediates of one clip, as numpy arrays laid out like the oracle's."""
+    lib = _lib.load()
+    dev = _device(device)
+    y = np.ascontiguousarray(y, dtype=np.float32)
+    n = int(y.size)
+    T = 1 + n // 512
+    with torch.cuda.device(dev):
+        _lib.check(lib.dys_init(), "dys_init")
+        d = torch.from_numpy(y).to(dev) if n else torch.zeros(4, device=dev)
+        power = torch.zeros((T, 1032), dtype=torch.float32, device=dev)
+        logmel = torch.zeros((T, 128), dtype=torch.float32, device=dev)
+        mfcc = torch.zeros((T, 20), dtype=torch.float32, device=dev)
+        chroma = torch.zeros((T, 12), dtype=torch.float32, device=dev)
+        scal = torch.zeros(4, dtype=torch.int32, device=dev)
+        out = torch.zeros(FEATURE_LEN, dtype=torch.float32, device=dev)
+        _lib.check(lib.dys_debug_feature_stages(d.data_ptr(), n, power.data_ptr(), logmel.data_ptr(), mfcc.data_ptr(),
+                                                chroma.data_ptr(), scal.data_ptr(), out.data_ptr(),
+                                                torch.cuda.current_stream(dev).cuda_stream), "dys_debug_feature_stages")
+        torch.cuda.synchronize(dev)
+        s = scal.cpu().numpy()
+    return dict(power=power[:, :1025].cpu().numpy().T, logmel_unclamped=logmel.cpu().numpy().T, mfcc=mfcc.cpu().numpy().T,
+                chroma=chroma.cpu().numpy().T, frames=int(s[0]), tuning_index=int(s[1]), peak_count=int(s[2]),
+                status=int(s[3]), features=out.cpu().numpy())
+
+
+def debug_denoise(y, prop_decrease: float = 1.0, device=None):
+    """-> (float32[n] reduce_noise output before normalisation, peak, fallback flag)."""
+    lib = _lib.load()
+    dev = _device(device)
+    y = np.ascontiguousarray(y, dtype=np.float32)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dys_init(), "dys_init")
+        d = torch.from_numpy(y).to(dev)
+        clean = torch.zeros_like(d)
+        info = torch.zeros(2, dtype=torch.float32, device=dev)
+        _lib.check(lib.dys_debug_denoise(d.data_ptr(), int(y.size), float(prop_decrease), clean.data_ptr(), info.data_ptr(),
+                                         torch.cuda.current_stream(dev).cuda_stream), "dys_debug_denoise")
+        torch.cuda.synchronize(dev)
+        i = info.cpu().numpy()
+    return clean.cpu().numpy(), float(i[0]), int(i[1])
+
+
+def get_table(which: int, arg: int = 0) -> np.ndarray:
+    """Host copy of a lookup table of the library (see dys_get_table in the header)."""
+    lib = _lib.load()
+    shapes = {0: ((128, 1025), np.float32), 1: ((20, 128), np.float32), 2: ((1025, 12), np.float32),
+              3: ((2048,), np.float32), 4: ((101,), np.float64), 5: ((40,), np.float64), 6: ((256,), np.float64),
+              7: ((1,), np.float64)}
+    shape, dt = shapes[which]
+    out = np.empty(shape, dtype=dt)
+    got = lib.dys_get_table(which, arg, out.ctypes.data, out.size)
+    if got != out.size:
+        raise DysError(f"dys_get_table({which}) returned {got}")
+    return out

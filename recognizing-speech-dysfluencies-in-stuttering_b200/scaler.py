@@ -1,0 +1,93 @@
+"""Global feature standardisation ("CMVN") across clips -- and across GPUs.
+
+Mirror of ``StandardScaler().fit(X)`` / ``.transform(X)`` in the reference
+(/root/reference/pipeline1.py:470-473; main1.py:848-852): float64 per-feature mean and
+population variance over ALL clips, ``scale_ = sqrt(var_)`` with constant features -> 1.0.
+
+Each rank reduces its own [N_rank, 149] feature block on the GPU (``dys_cmvn_accumulate``)
+to 299 doubles; the ONE collective of the whole path is a sum all-reduce of that vector
+(NCCL over NVLink when ranks are GPUs; gloo in the CPU tests).  Two passes (mean, then moments
+about the mean) reproduce sklearn's corrected two-pass variance.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import CMVN_ACC_LEN, CMVN_PARTIALS, FEATURE_LEN
+
+
+def _allreduce_sum(vec: torch.Tensor, group) -> torch.Tensor:
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        backend = dist.get_backend(group)
+        if backend == "gloo" and vec.is_cuda:
+            host = vec.cpu()
+            dist.all_reduce(host, op=dist.ReduceOp.SUM, group=group)
+            vec.copy_(host)
+        else:
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+    return vec
+
+
+def merge_moments(parts):
+    """Host-side merge used by the gloo tests: sum of per-rank [n, S1, S2] vectors."""
+    return np.sum(np.stack([np.asarray(p, dtype=np.float64) for p in parts]), axis=0)
+
+
+class GlobalScaler:
+    """``fit`` / ``transform`` with sklearn's attribute names (mean_, var_, scale_, n_samples_seen_)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.mean_ = self.var_ = self.scale_ = None
+        self.n_samples_seen_ = 0
+
+    def _moments(self, X: torch.Tensor, shift: torch.Tensor | None) -> torch.Tensor:
+        lib = _lib.load()
+        acc = torch.empty(CMVN_ACC_LEN, dtype=torch.float64, device=X.device)
+        partials = torch.empty(CMVN_PARTIALS, dtype=torch.float64, device=X.device)
+        with torch.cuda.device(X.device):
+            _lib.check(lib.dys_cmvn_accumulate(X.data_ptr() if X.numel() else None, X.shape[0],
+                                               shift.data_ptr() if shift is not None else None, acc.data_ptr(),
+                                               partials.data_ptr(), torch.cuda.current_stream(X.device).cuda_stream),
+                       "dys_cmvn_accumulate")
+        return acc
+
+    def fit(self, X: torch.Tensor):
+        """X: this rank's float32 [N_rank, 149] CUDA tensor. Collective when torch.distributed is initialised."""
+        if not (isinstance(X, torch.Tensor) and X.is_cuda and X.dtype == torch.float32 and X.dim() == 2
+                and X.shape[1] == FEATURE_LEN):
+            raise ValueError("X must be a float32 CUDA tensor of shape [N, 149]")
+        X = X.contiguous()
+        lib = _lib.load()
+        acc0 = _allreduce_sum(self._moments(X, None), self.group)
+        n = acc0[0]
+        mean0 = (acc0[1:1 + FEATURE_LEN] / n).contiguous()
+        acc1 = _allreduce_sum(self._moments(X, mean0), self.group)
+        mean = torch.empty(FEATURE_LEN, dtype=torch.float64, device=X.device)
+        scale = torch.empty(FEATURE_LEN, dtype=torch.float64, device=X.device)
+        with torch.cuda.device(X.device):
+            _lib.check(lib.dys_cmvn_finalize(acc1.data_ptr(), mean0.data_ptr(), mean.data_ptr(), scale.data_ptr(),
+                                             torch.cuda.current_stream(X.device).cuda_stream), "dys_cmvn_finalize")
+        m1 = acc1[1:1 + FEATURE_LEN] / n
+        self.var_ = torch.clamp(acc1[1 + FEATURE_LEN:] / n - m1 * m1, min=0.0)
+        self.mean_, self.scale_ = mean, scale
+        self.n_samples_seen_ = int(n.item())
+        return self
+
+    def transform(self, X: torch.Tensor) -> torch.Tensor:
+        if self.mean_ is None:
+            raise RuntimeError("GlobalScaler.transform called before fit")
+        lib = _lib.load()
+        X = X.contiguous()
+        out = torch.empty_like(X)
+        with torch.cuda.device(X.device):
+            _lib.check(lib.dys_cmvn_apply(X.data_ptr() if X.numel() else None, X.shape[0], self.mean_.data_ptr(),
+                                          self.scale_.data_ptr(), out.data_ptr() if X.numel() else None,
+                                          torch.cuda.current_stream(X.device).cuda_stream), "dys_cmvn_apply")
+        return out
+
+    def fit_transform(self, X: torch.Tensor) -> torch.Tensor:
+        return self.fit(X).transform(X)

@@ -1,0 +1,100 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol the header
+declares, its lookup tables equal the oracle's, and the host layer fails loudly without a GPU."""
+import ctypes
+import importlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import PKG_NAME, ROOT
+from oracle import denoise, features
+
+
+def test_package_imports_without_gpu(pkg):
+    assert pkg.FEATURE_LEN == 149
+    alias = importlib.import_module("dysb200")
+    assert alias is pkg
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    header = open(os.path.join(ROOT, "include", "dysfluency_b200.h")).read()
+    declared = set(re.findall(r"DYS_API\s+[\w\s\*]+?\b(dys_\w+)\s*\(", header))
+    assert len(declared) >= 13
+    assert declared == set(pkg._lib.EXPORTED_SYMBOLS)
+    lib = ctypes.CDLL(pkg._lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    loaded = pkg._lib.load()
+    assert loaded.dys_version() == 100
+    assert loaded.dys_last_error() == b""
+
+
+def test_workspace_queries(pkg):
+    lib = pkg._lib.load()
+    need = lib.dys_workspace_bytes(64, 48000, 1)
+    least = lib.dys_workspace_min_bytes(64, 48000, 1)
+    assert 0 < least <= need
+    assert lib.dys_workspace_bytes(64, 48000, 0) < need
+    assert lib.dys_workspace_bytes(-1, 10, 0) == -1
+
+
+def test_tables_match_oracle(pkg):
+    fe = pkg.frontend
+    assert np.array_equal(fe.get_table(0), features.mel_filterbank())
+    np.testing.assert_allclose(fe.get_table(1), features.dct_matrix(), atol=1e-8)
+    for ti in (0, 13, 50, 99):
+        np.testing.assert_array_equal(fe.get_table(2, ti), features.chroma_filterbank(float(features.TUNING_EDGES[ti])).T)
+    assert np.array_equal(fe.get_table(3), features.hann_periodic(2048).astype(np.float32))
+    assert np.array_equal(fe.get_table(4), features.TUNING_EDGES)
+    taps = fe.get_table(5)
+    np.testing.assert_allclose(np.outer(taps[:33], taps[33:]), denoise.smoothing_filter(), atol=1e-17)
+    assert np.array_equal(fe.get_table(6), denoise._window_sumsquare(20)[1024:1280])
+    assert fe.get_table(7)[0] == denoise.iir_coefficient()
+
+
+def test_no_cpu_fallback(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    fe = pkg.frontend
+    y = np.zeros(48000, np.float32)
+    with pytest.raises(pkg.DysError):
+        fe.extract_features_batch([y])
+    with pytest.raises(pkg.DysError):
+        fe.extract_features(y, 16000)
+    # the C ABI itself refuses too
+    assert pkg._lib.load().dys_init() != 0
+    assert b"CUDA" in pkg._lib.load().dys_last_error() or b"device" in pkg._lib.load().dys_last_error()
+
+
+def test_text_features_and_errors(pkg):
+    fe = pkg.frontend
+    assert not fe.extract_text_features("").any()
+    v = fe.extract_text_features("the the cat sat sat sat")
+    assert v.dtype == np.float32 and v.tolist()[:3] == [23.0, 6.0, 3.0]
+    assert fe.load_audio("/nonexistent/file.wav") == (None, None)
+    with pytest.raises(ValueError):
+        fe.extract_features_batch([np.zeros(10, np.float32)], sr=22050)
+
+
+def test_sharding_and_windows(pkg):
+    sh = pkg.sharding
+    for n, w in ((10000, 8), (7, 3), (5, 8)):
+        ranges = [sh.shard_range(n, r, w) for r in range(w)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+    assert len(sh.sliding_windows(57_600_000)) == 2399          # BASELINE config 4
+    assert sh.sliding_windows(47999) == []
+
+
+def test_wav_io_round_trip(pkg, tmp_path):
+    q = (np.random.default_rng(0).integers(-32768, 32767, 1000)).astype(np.int16)
+    p = tmp_path / "a.wav"
+    pkg.wavio.write_wav_pcm16(str(p), q)
+    y, sr = pkg.wavio.read_wav(str(p))
+    assert sr == 16000 and np.array_equal(y, q.astype(np.float32) / 32768)
+    from oracle import wavio as owav
+    back, _ = owav.read_wav_pcm16(str(p))
+    assert np.array_equal(back, q)
