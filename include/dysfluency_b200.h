@@ -116,6 +116,17 @@ DYS_API int dys_debug_feature_stages(const float* d_audio, int32_t n, float* d_p
 /* Denoise ONE clip: d_clean float32[n] (reduce_noise output, before normalisation), d_info float32[2] = {peak, flag}. */
 DYS_API int dys_debug_denoise(const float* d_audio, int32_t n, float prop_decrease, float* d_clean, float* d_info, void* stream);
 
+/* ---- launch accounting (bench.py: "gpu_launches" and the live roofline timing) ---- */
+/* Number of distinct kernels in the library; dys_kernel_name(i) names kernel i ("" out of range). */
+DYS_API int dys_kernel_count(void);
+DYS_API const char* dys_kernel_name(int32_t index);
+/* on != 0: bracket every kernel launch with two cudaEvents on its stream (adds no synchronisation). */
+DYS_API int dys_profile_enable(int32_t on);
+/* Waits for the recorded events; h_ms[i] = total milliseconds spent in kernel i since the last reset
+ * (only while profiling was enabled), h_launches[i] = launches of kernel i since the last reset (always
+ * counted).  Both are HOST arrays of dys_kernel_count() elements; either may be NULL. */
+DYS_API int dys_profile_read(double* h_ms, int64_t* h_launches, int32_t reset);
+
 #ifdef __cplusplus
 }
 #endif

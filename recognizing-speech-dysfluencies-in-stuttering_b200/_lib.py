@@ -35,6 +35,10 @@ _SIGNATURES = {
     "dys_get_table": (_i64, [_i32, _i32, _vp, _i64]),
     "dys_debug_feature_stages": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dys_debug_denoise": (C.c_int, [_vp, _i32, _f32, _vp, _vp, _vp]),
+    "dys_kernel_count": (C.c_int, []),
+    "dys_kernel_name": (C.c_char_p, [_i32]),
+    "dys_profile_enable": (C.c_int, [_i32]),
+    "dys_profile_read": (C.c_int, [_vp, _vp, _i32]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 
@@ -66,3 +70,22 @@ def check(rc: int, what: str):
     if rc != OK:
         msg = load().dys_last_error().decode("utf-8", "replace")
         raise DysError(f"{what} failed (code {rc}): {msg}")
+
+
+def kernel_names():
+    lib = load()
+    return [lib.dys_kernel_name(i).decode() for i in range(lib.dys_kernel_count())]
+
+
+def profile_enable(on: bool):
+    check(load().dys_profile_enable(1 if on else 0), "dys_profile_enable")
+
+
+def profile_read(reset: bool = True):
+    """-> {kernel name: (total ms while profiling was on, launches)} since the last reset."""
+    lib = load()
+    n = lib.dys_kernel_count()
+    ms = (C.c_double * n)()
+    cnt = (C.c_int64 * n)()
+    check(lib.dys_profile_read(C.cast(ms, C.c_void_p), C.cast(cnt, C.c_void_p), 1 if reset else 0), "dys_profile_read")
+    return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(kernel_names())}

@@ -8,6 +8,7 @@
 #include "../../include/dysfluency_b200.h"
 #include "dys_error.h"
 #include "dys_kernels.h"
+#include "dys_profile.h"
 
 namespace dys {
 
@@ -312,6 +313,23 @@ DYS_API int dys_debug_denoise(const float* d_audio, int32_t n, float prop_decrea
     }
     cudaFree(ws);
     if (e != cudaSuccess) { set_error(std::string("debug_denoise: ") + cudaGetErrorString(e)); return DYS_ERR_CUDA; }
+    return DYS_OK;
+}
+
+DYS_API int dys_kernel_count(void) { return kKernelCount; }
+
+DYS_API const char* dys_kernel_name(int32_t index) { return kernel_name(index); }
+
+DYS_API int dys_profile_enable(int32_t on) {
+    profile_enable(on != 0);
+    return DYS_OK;
+}
+
+DYS_API int dys_profile_read(double* h_ms, int64_t* h_launches, int32_t reset) {
+    long long counts[kKernelCount];
+    DYS_CUDA_OK(profile_read(h_ms, counts, reset));
+    if (h_launches)
+        for (int i = 0; i < kKernelCount; ++i) h_launches[i] = counts[i];
     return DYS_OK;
 }
 

@@ -10,6 +10,7 @@
 #include <cmath>
 
 #include "dys_kernels.h"
+#include "dys_profile.h"
 
 namespace dys {
 
@@ -77,12 +78,15 @@ __global__ void k_cmvn_apply(const float* __restrict__ feats, int64_t n_rows, co
 
 cudaError_t launch_cmvn_accumulate(const float* feats, int64_t n_rows, const double* shift, double* acc, double* partials,
                                    cudaStream_t stream) {
-    k_cmvn_partial<<<kCmvnPartials, 160, 0, stream>>>(feats, n_rows, shift, partials);
-    k_cmvn_merge<<<1, 160, 0, stream>>>(partials, kCmvnPartials, n_rows, acc);
+    { LaunchScope ls(kK_cmvn_partial, stream);
+      k_cmvn_partial<<<kCmvnPartials, 160, 0, stream>>>(feats, n_rows, shift, partials); }
+    { LaunchScope ls(kK_cmvn_merge, stream);
+      k_cmvn_merge<<<1, 160, 0, stream>>>(partials, kCmvnPartials, n_rows, acc); }
     return cudaGetLastError();
 }
 
 cudaError_t launch_cmvn_finalize(const double* acc, const double* shift, double* mean, double* scale, cudaStream_t stream) {
+    LaunchScope ls(kK_cmvn_finalize, stream);
     k_cmvn_finalize<<<1, 160, 0, stream>>>(acc, shift, mean, scale);
     return cudaGetLastError();
 }
@@ -91,6 +95,7 @@ cudaError_t launch_cmvn_apply(const float* feats, int64_t n_rows, const double* 
                               cudaStream_t stream) {
     const int64_t total = n_rows * kFeat;
     if (total <= 0) return cudaSuccess;
+    LaunchScope ls(kK_cmvn_apply, stream);
     k_cmvn_apply<<<unsigned((total + 255) / 256), 256, 0, stream>>>(feats, n_rows, mean, scale, out);
     return cudaGetLastError();
 }

@@ -23,6 +23,7 @@
 
 #include "dys_fft.cuh"
 #include "dys_kernels.h"
+#include "dys_profile.h"
 
 namespace dys {
 
@@ -403,6 +404,7 @@ void nr_scratch_carve(void* base, int n_items, int ta_max, NrScratch* out) {
 
 cudaError_t launch_clean_init(const ClipView& cv, float* clean_peak, int32_t* clean_flag, cudaStream_t stream) {
     if (cv.n_clips <= 0) return cudaSuccess;
+    LaunchScope ls(kK_clean_init, stream);
     k_clean_init<<<(cv.n_clips + 255) / 256, 256, 0, stream>>>(clean_peak, clean_flag, cv);
     return cudaGetLastError();
 }
@@ -423,20 +425,26 @@ cudaError_t launch_denoise(const DeviceTables& tb, const ClipView& cv, float* cl
     const int gy = (sc.ta_max + kFramesPerCta - 1) / kFramesPerCta;
     ClipView cvw = cv;
     cvw.clean = clean; cvw.clean_peak = clean_peak; cvw.clean_flag = clean_flag;
-    k_nr_stft_mag<<<dim3(n_items, gy), kThreads, sizeof(NrSmem), stream>>>(tb, cvw, cpc, item0, sc);
-    k_nr_iir_mask<<<dim3(n_items, (kNrBins + 127) / 128), 128, 0, stream>>>(tb, cvw, cpc, item0, sc, clean_flag);
-    k_nr_smooth<<<dim3(n_items, (sc.ta_max + kSmoothRows - 1) / kSmoothRows), kThreads, 0, stream>>>(tb, cvw, cpc, item0, sc,
-                                                                                                    double(prop_decrease));
-    k_nr_apply_istft<<<dim3(n_items, gy), kThreads, sizeof(NrSmem), stream>>>(tb, cvw, cpc, item0, sc);
+    { LaunchScope ls(kK_nr_stft_mag, stream);
+      k_nr_stft_mag<<<dim3(n_items, gy), kThreads, sizeof(NrSmem), stream>>>(tb, cvw, cpc, item0, sc); }
+    { LaunchScope ls(kK_nr_iir_mask, stream);
+      k_nr_iir_mask<<<dim3(n_items, (kNrBins + 127) / 128), 128, 0, stream>>>(tb, cvw, cpc, item0, sc, clean_flag); }
+    { LaunchScope ls(kK_nr_smooth, stream);
+      k_nr_smooth<<<dim3(n_items, (sc.ta_max + kSmoothRows - 1) / kSmoothRows), kThreads, 0, stream>>>(tb, cvw, cpc, item0, sc,
+                                                                                                      double(prop_decrease)); }
+    { LaunchScope ls(kK_nr_apply_istft, stream);
+      k_nr_apply_istft<<<dim3(n_items, gy), kThreads, sizeof(NrSmem), stream>>>(tb, cvw, cpc, item0, sc); }
     const int max_out = std::min(cv.max_len, kNrChunk);
-    k_nr_overlap_add<<<dim3(n_items, (max_out + 255) / 256), 256, 0, stream>>>(tb, cvw, cpc, item0, sc, clean, clean_peak,
-                                                                             clean_flag);
+    { LaunchScope ls(kK_nr_overlap_add, stream);
+      k_nr_overlap_add<<<dim3(n_items, (max_out + 255) / 256), 256, 0, stream>>>(tb, cvw, cpc, item0, sc, clean, clean_peak,
+                                                                               clean_flag); }
     return cudaGetLastError();
 }
 
 cudaError_t launch_quantize_pcm(const ClipView& cv, int16_t* pcm, const int64_t* pcm_starts, cudaStream_t stream) {
     if (cv.n_clips <= 0) return cudaSuccess;
     const int gy = std::max(1, std::min(64, (cv.max_len + 255) / 256));
+    LaunchScope ls(kK_quantize_pcm, stream);
     k_quantize_pcm<<<dim3(cv.n_clips, gy), 256, 0, stream>>>(cv, pcm, pcm_starts);
     return cudaGetLastError();
 }

@@ -21,6 +21,7 @@
 
 #include "dys_fft.cuh"
 #include "dys_kernels.h"
+#include "dys_profile.h"
 
 namespace dys {
 
@@ -524,11 +525,16 @@ cudaError_t launch_features(const DeviceTables& tb, const ClipView& cv, int inst
         attr_set[dev & 63] = true;
     }
     const int gx = (sc.t_max + kFramesPerCta - 1) / kFramesPerCta;
-    k_feat_init<<<(n_inst + 255) / 256, 256, 0, stream>>>(sc.peak_count, sc.lmax_enc, status, cv, inst0, n_inst);
-    k_frame_spectra<<<dim3(n_inst, gx), kThreads, sizeof(SpectraSmem), stream>>>(tb, cv, inst0, sc, status);
-    k_tuning<<<n_inst, 256, 0, stream>>>(tb, sc);
-    k_frame_cepstra<<<dim3(n_inst, gx), kThreads, 0, stream>>>(tb, cv, inst0, sc);
-    k_clip_stats<<<n_inst, 256, 0, stream>>>(cv, inst0, sc, out_raw, out_clean, status);
+    { LaunchScope ls(kK_feat_init, stream);
+      k_feat_init<<<(n_inst + 255) / 256, 256, 0, stream>>>(sc.peak_count, sc.lmax_enc, status, cv, inst0, n_inst); }
+    { LaunchScope ls(kK_frame_spectra, stream);
+      k_frame_spectra<<<dim3(n_inst, gx), kThreads, sizeof(SpectraSmem), stream>>>(tb, cv, inst0, sc, status); }
+    { LaunchScope ls(kK_tuning, stream);
+      k_tuning<<<n_inst, 256, 0, stream>>>(tb, sc); }
+    { LaunchScope ls(kK_frame_cepstra, stream);
+      k_frame_cepstra<<<dim3(n_inst, gx), kThreads, 0, stream>>>(tb, cv, inst0, sc); }
+    { LaunchScope ls(kK_clip_stats, stream);
+      k_clip_stats<<<n_inst, 256, 0, stream>>>(cv, inst0, sc, out_raw, out_clean, status); }
     return cudaGetLastError();
 }
 

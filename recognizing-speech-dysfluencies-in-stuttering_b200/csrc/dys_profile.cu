@@ -1,0 +1,83 @@
+#include "dys_profile.h"
+
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+namespace dys {
+
+namespace {
+
+const char* const kNames[kKernelCount] = {
+    "k_feat_init", "k_frame_spectra", "k_tuning", "k_frame_cepstra", "k_clip_stats", "k_clean_init",
+    "k_nr_stft_mag", "k_nr_iir_mask", "k_nr_smooth", "k_nr_apply_istft", "k_nr_overlap_add", "k_quantize_pcm",
+    "k_cmvn_partial", "k_cmvn_merge", "k_cmvn_finalize", "k_cmvn_apply"};
+
+struct Record {
+    int id;
+    cudaEvent_t start, stop;
+};
+
+std::atomic<long long> g_launches[kKernelCount];
+std::atomic<bool> g_enabled{false};
+std::mutex g_mu;
+std::vector<Record> g_records;          // events in flight (not yet read)
+std::vector<cudaEvent_t> g_free;        // recycled events
+double g_ms[kKernelCount] = {};
+
+cudaEvent_t take_event() {
+    if (!g_free.empty()) {
+        cudaEvent_t e = g_free.back();
+        g_free.pop_back();
+        return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+}  // namespace
+
+const char* kernel_name(int id) { return (id >= 0 && id < kKernelCount) ? kNames[id] : ""; }
+
+LaunchScope::LaunchScope(int id, cudaStream_t stream) : slot_(-1), stream_(stream) {
+    g_launches[id].fetch_add(1, std::memory_order_relaxed);
+    if (!g_enabled.load(std::memory_order_relaxed)) return;
+    std::lock_guard<std::mutex> lock(g_mu);
+    Record r{id, take_event(), take_event()};
+    if (!r.start || !r.stop) return;
+    cudaEventRecord(r.start, stream);
+    slot_ = int(g_records.size());
+    g_records.push_back(r);
+}
+
+LaunchScope::~LaunchScope() {
+    if (slot_ < 0) return;
+    std::lock_guard<std::mutex> lock(g_mu);
+    cudaEventRecord(g_records[slot_].stop, stream_);
+}
+
+void profile_enable(bool on) { g_enabled.store(on); }
+
+cudaError_t profile_read(double* ms, long long* launches, int reset) {
+    std::lock_guard<std::mutex> lock(g_mu);
+    cudaError_t err = cudaSuccess;
+    for (const Record& r : g_records) {
+        cudaError_t e = cudaEventSynchronize(r.stop);
+        float t = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&t, r.start, r.stop);
+        if (e == cudaSuccess) g_ms[r.id] += double(t);
+        else err = e;
+        g_free.push_back(r.start);
+        g_free.push_back(r.stop);
+    }
+    g_records.clear();
+    for (int i = 0; i < kKernelCount; ++i) {
+        if (ms) ms[i] = g_ms[i];
+        if (launches) launches[i] = g_launches[i].load();
+        if (reset) { g_ms[i] = 0.0; g_launches[i].store(0); }
+    }
+    return err;
+}
+
+}  // namespace dys

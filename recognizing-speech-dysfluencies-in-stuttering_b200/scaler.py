@@ -31,9 +31,27 @@ def _allreduce_sum(vec: torch.Tensor, group) -> torch.Tensor:
     return vec
 
 
-def merge_moments(parts):
-    """Host-side merge used by the gloo tests: sum of per-rank [n, S1, S2] vectors."""
-    return np.sum(np.stack([np.asarray(p, dtype=np.float64) for p in parts]), axis=0)
+def allreduce_moments(acc: torch.Tensor, group=None) -> torch.Tensor:
+    """The path's one collective: in-place sum all-reduce of a rank's float64 [299] moment vector
+    ([n, sum_f (x - s), sum_f (x - s)^2]) over the process group (NCCL on GPUs, gloo on CPU)."""
+    if acc.dtype != torch.float64 or acc.numel() != CMVN_ACC_LEN:
+        raise ValueError("acc must be a float64 vector of 299 elements")
+    return _allreduce_sum(acc, group)
+
+
+def finalize_moments(acc, shift=None):
+    """Host float64 mirror of dys_cmvn_finalize: (mean, var, scale, n) from all-reduced moments about
+    ``shift`` (None = 0); constant features get scale 1.0 like sklearn's StandardScaler."""
+    acc = np.asarray(acc.cpu() if isinstance(acc, torch.Tensor) else acc, dtype=np.float64)
+    n = acc[0]
+    m1 = acc[1:1 + FEATURE_LEN] / n
+    mean = m1 + (0.0 if shift is None else np.asarray(shift, dtype=np.float64))
+    var = np.maximum(acc[1 + FEATURE_LEN:] / n - m1 * m1, 0.0)
+    eps = np.finfo(np.float64).eps
+    scale = np.sqrt(var)
+    const = (var <= n * eps * var + (n * mean * eps) ** 2) | (scale < 10 * eps)
+    scale[const] = 1.0
+    return mean, var, scale, int(n)
 
 
 class GlobalScaler:
@@ -42,7 +60,7 @@ class GlobalScaler:
     def __init__(self, group=None):
         self.group = group
         self.mean_ = self.var_ = self.scale_ = None
-        self.n_samples_seen_ = 0
+        self._n = None
 
     def _moments(self, X: torch.Tensor, shift: torch.Tensor | None) -> torch.Tensor:
         lib = _lib.load()
@@ -74,8 +92,12 @@ class GlobalScaler:
         m1 = acc1[1:1 + FEATURE_LEN] / n
         self.var_ = torch.clamp(acc1[1 + FEATURE_LEN:] / n - m1 * m1, min=0.0)
         self.mean_, self.scale_ = mean, scale
-        self.n_samples_seen_ = int(n.item())
+        self._n = n                      # device scalar: reading it would force a host sync inside fit()
         return self
+
+    @property
+    def n_samples_seen_(self) -> int:
+        return 0 if self._n is None else int(self._n.item())
 
     def transform(self, X: torch.Tensor) -> torch.Tensor:
         if self.mean_ is None:

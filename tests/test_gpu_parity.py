@@ -1,0 +1,346 @@
+"""Parity tests proper: the CUDA path (through the C ABI of libdysb200.so) against the CPU oracle,
+the reference's committed golden vectors, and size-independent properties at bench scale.
+
+Tolerances (BASELINE.json north_star): frame counts / shapes / status flags / int16 PCM bit-exact;
+MFCC, delta, delta-delta statistics within atol 1e-3 + rtol 1e-4 in fp32.  Chroma depends on a
+DISCRETE per-clip decision (1-of-100 tuning bin: median threshold + histogram arg-max, SURVEY.md
+section 7 hard part 3): where the tuning bin agrees the chroma statistics are held to atol 1e-4,
+and the number of clips whose bin flips is bounded and reported.
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cmvn as ocmvn
+from oracle import denoise as oden
+from oracle import features as ofeat
+from oracle import wavio as owav
+
+pytestmark = pytest.mark.gpu
+
+ATOL, RTOL = 1e-3, 1e-4
+CHROMA_ATOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("the -m gpu tests need a CUDA device (there is no CPU fallback to test)")
+    torch.cuda.set_device(0)
+    return torch
+
+
+@pytest.fixture(scope="module")
+def fe(pkg, torch_cuda):
+    lib = pkg._lib.load()           # fails loudly when libdysb200.so was not built
+    assert lib.dys_init() == 0, lib.dys_last_error()
+    return pkg.frontend
+
+
+def _assert_feature_parity(got, ref, what, chroma_flips=None):
+    """MFCC/delta/delta2 block to the north-star tolerance; chroma to CHROMA_ATOL unless the tuning bin flipped."""
+    assert got.shape == ref.shape == (149,) and got.dtype == np.float32
+    np.testing.assert_allclose(got[:120], ref[:120], atol=ATOL, rtol=RTOL, err_msg=f"{what}: mfcc/delta block")
+    assert not got[144:].any()
+    cerr = float(np.abs(got[120:144] - ref[120:144]).max())
+    if cerr > CHROMA_ATOL:
+        if chroma_flips is None:
+            raise AssertionError(f"{what}: chroma err {cerr:.3e}")
+        chroma_flips.append((what, cerr))
+
+
+# ---------------------------------------------------------------------------------------------
+# config 1: 64 synthetic 3-s clips + edge set, raw + clean, against the oracle
+# ---------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def config1(fe, synth):
+    clips = [synth.synth_clip(i) for i in range(64)]
+    names = [f"synth{i}" for i in range(64)]
+    for name, y in synth.edge_clips():
+        clips.append(y)
+        names.append(name)
+    raw, clean, status, pcm = fe.extract_features_batch(clips, denoise=True, return_status=True, return_pcm=True)
+    return dict(clips=clips, names=names, raw=raw.cpu().numpy(), clean=clean.cpu().numpy(),
+                status=status.cpu().numpy(), pcm=[p.cpu().numpy() for p in pcm])
+
+
+def test_config1_raw_features_match_oracle(config1):
+    flips = []
+    for i, (name, y) in enumerate(zip(config1["names"], config1["clips"])):
+        ref = ofeat.extract_features(y)
+        if name == "impulse":
+            # flat spectrum: every bin ties, piptrack's strict/weak local-max test is decided by rounding
+            # noise -> the tuning bin is ill-defined; only the MFCC block is comparable.
+            np.testing.assert_allclose(config1["raw"][i][:120], ref[:120], atol=ATOL, rtol=RTOL)
+            continue
+        _assert_feature_parity(config1["raw"][i], ref, name, flips)
+    assert len(flips) <= 1, flips
+
+
+def test_config1_status_flags_and_zero_rows(config1, pkg):
+    n = len(config1["clips"])
+    st = config1["status"]
+    for i, name in enumerate(config1["names"]):
+        if name == "len4095":                       # T = 8 < 9 frames -> zeros(144) on both branches
+            assert st[i] & pkg.STATUS_SHORT and st[n + i] & pkg.STATUS_SHORT
+            assert not config1["raw"][i].any() and not config1["clean"][i].any()
+        elif name == "all_zero":                    # 0/0 -> NaN -> normalize raises -> raw file used as clean
+            assert st[i] == 0 and st[n + i] == pkg.STATUS_CLEAN_FALLBACK
+            np.testing.assert_array_equal(config1["raw"][i], config1["clean"][i])
+        else:
+            assert st[i] == 0 and st[n + i] == 0, (name, st[i], st[n + i])
+
+
+def test_config1_clean_pcm_bit_exact_and_features(config1):
+    """Denoise runs in float64 like noisereduce, so the PCM-16 the reference would write must be
+    reproduced sample for sample; then the clean features follow to the same tolerance as raw."""
+    flips = []
+    total = mism = 0
+    for i, (name, y) in enumerate(zip(config1["names"], config1["clips"])):
+        if i >= 16 and not name.startswith(("len", "dc", "square")):
+            continue                                 # oracle denoise ~50 ms/clip: 16 synthetic + edges
+        q_ref = oden.clean_audio(y)
+        if q_ref is None:
+            continue
+        q = config1["pcm"][i]
+        assert q.dtype == np.int16 and q.shape == q_ref.shape          # length preserved
+        total += q.size
+        mism += int((q != q_ref).sum())
+        assert np.abs(q.astype(np.int32) - q_ref.astype(np.int32)).max() <= 1, name
+        ref = ofeat.extract_features(owav.dequantize_pcm16(q_ref))
+        _assert_feature_parity(config1["clean"][i], ref, name + "/clean", flips)
+    assert total > 0 and mism <= total * 1e-5, f"{mism} of {total} PCM samples differ"
+    assert len(flips) <= 1, flips
+
+
+def test_stagewise_intermediates(fe, synth):
+    """power, log-mel, MFCC, tuning, chroma exposed and compared."""
+    for seed, n in ((0, 48000), (5, 47999), (11, 160000), (12, 4096)):
+        y = synth.synth_clip(seed, n)
+        it = ofeat.intermediates(y)
+        g = fe.debug_feature_stages(y)
+        T = 1 + n // 512
+        assert g["frames"] == T and g["power"].shape == (1025, T) == it["power"].shape       # bit-exact shapes
+        assert np.abs(g["power"] - it["power"]).max() <= 2e-6 * it["power"].max()
+        Lu = 10 * np.log10(np.maximum(1e-10, it["mel"]))
+        np.testing.assert_allclose(g["logmel_unclamped"], Lu, atol=ATOL, rtol=RTOL)
+        np.testing.assert_allclose(g["mfcc"], it["mfcc"], atol=ATOL, rtol=RTOL)
+        assert g["peak_count"] == len(ofeat.piptrack_peaks(it["power"])[0])
+        assert g["tuning_index"] == ofeat.tuning_index(it["tuning"])
+        np.testing.assert_allclose(g["chroma"], it["chroma"], atol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own golden vectors (committed fixtures; /root/reference is absent on the GPU box)
+# ---------------------------------------------------------------------------------------------
+def test_reference_golden_pairs(fe, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_clean_pairs.npz"))
+    offs = g["offsets"]
+    clips = [owav.dequantize_pcm16(g["pcm"][offs[i]:offs[i + 1]]) for i in range(len(offs) - 1)]
+    got = fe.extract_features_batch(clips).cpu().numpy()          # ragged batch, T = 14 .. 316 frames
+    flips = []
+    for i in range(len(clips)):
+        _assert_feature_parity(got[i], g["feats"][i], str(g["names"][i]), flips)
+    assert len(flips) <= 1, flips
+    # and through the reference-named single-clip entry point
+    one = fe.extract_features(clips[3], 16000)
+    np.testing.assert_array_equal(one, got[3])
+
+
+def test_scaler_golden(fe, pkg, torch_cuda, golden_dir):
+    g = np.load(os.path.join(golden_dir, "ref_scaler_after.npz"))
+    X = torch_cuda.from_numpy(g["X"]).cuda()
+    sc = pkg.scaler.GlobalScaler().fit(X)
+    assert sc.n_samples_seen_ == 905
+    np.testing.assert_allclose(sc.mean_.cpu().numpy(), g["mean"], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(sc.var_.cpu().numpy(), g["var"], rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(sc.scale_.cpu().numpy(), g["scale"], rtol=1e-11, atol=1e-13)
+    assert np.all(sc.scale_.cpu().numpy()[144:] == 1.0)
+    Z = sc.transform(X).cpu().numpy()
+    ref = ocmvn.transform(g["X"], g["mean"], g["scale"]).astype(np.float32)
+    np.testing.assert_allclose(Z, ref, atol=2e-6, rtol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------------------
+def test_ragged_empty_and_invalid_inputs(fe, pkg, synth, torch_cuda):
+    assert fe.extract_features_batch([]).shape == (0, 149)
+    bad = synth.synth_clip(3, 8000)
+    bad[17] = np.nan
+    clips = [synth.synth_clip(1, 4607), np.zeros(0, np.float32), bad, synth.synth_clip(2, 4608), synth.synth_clip(4, 1)]
+    raw, clean, st = fe.extract_features_batch(clips, denoise=True, return_status=True)
+    raw, clean, st = raw.cpu().numpy(), clean.cpu().numpy(), st.cpu().numpy()
+    assert st[1] & pkg.STATUS_SHORT and st[4] & pkg.STATUS_SHORT and not raw[1].any() and not raw[4].any()
+    assert st[2] & pkg.STATUS_NONFINITE and not raw[2].any()
+    for i in (0, 3):
+        _assert_feature_parity(raw[i], ofeat.extract_features(clips[i]), f"ragged{i}")
+    # the reference-named wrappers keep the reference's "never raise, return zeros" convention
+    assert not fe.extract_features(None, 16000).any()
+    assert not fe.extract_audio_features(np.zeros(0, np.float32), 16000).any()
+    assert fe.clean_audio(np.zeros(48000, np.float32)) is None
+
+
+def test_chunked_denoise_long_clip(fe, synth):
+    """> 600 000 samples: noisereduce gates 600 000-sample chunks with 30 000 samples of real overlap."""
+    y = np.tile(synth.synth_clip(1), 13)[:610000]
+    got, peak, flag = fe.debug_denoise(y)
+    ref = oden.reduce_noise(y)
+    assert flag == 0 and got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 2e-7 * np.abs(ref).max()
+    assert peak == pytest.approx(float(np.abs(ref).max()), rel=1e-6)
+
+
+def test_prop_decrease_variants(fe, synth):
+    """main1.py:605 uses prop_decrease=0.8; 0.0 must leave the clip (perfect STFT/ISTFT reconstruction)."""
+    y = synth.synth_clip(21)
+    got, _, _ = fe.debug_denoise(y, prop_decrease=0.8)
+    ref = oden.reduce_noise(y, prop_decrease=0.8)
+    assert np.abs(got - ref).max() <= 2e-7 * np.abs(ref).max()
+    same, _, _ = fe.debug_denoise(y, prop_decrease=0.0)
+    np.testing.assert_allclose(same, y, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# the C ABI called directly (plain pointers + sizes; no host-layer help)
+# ---------------------------------------------------------------------------------------------
+def test_c_abi_direct_and_workspace_contract(pkg, fe, synth, torch_cuda):
+    torch = torch_cuda
+    lib = pkg._lib.load()
+    X = synth.synth_batch(6)
+    n, L = X.shape
+    d_audio = torch.from_numpy(X).cuda().reshape(-1)
+    d_starts = (torch.arange(n, dtype=torch.int64) * L).cuda()
+    d_lens = torch.full((n,), L, dtype=torch.int32, device="cuda")
+    outs = []
+    for ws_bytes in (lib.dys_workspace_bytes(n, L, 1), lib.dys_workspace_min_bytes(n, L, 1)):
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+        raw = torch.full((n, 149), 7.0, device="cuda")
+        clean = torch.full((n, 149), 7.0, device="cuda")
+        st = torch.full((2 * n,), -1, dtype=torch.int32, device="cuda")
+        rc = lib.dys_features_raw_clean(d_audio.data_ptr(), d_starts.data_ptr(), d_lens.data_ptr(), n, L,
+                                        ctypes.c_float(1.0), raw.data_ptr(), clean.data_ptr(), st.data_ptr(), None, None,
+                                        ws.data_ptr(), ws_bytes, None)
+        assert rc == 0, lib.dys_last_error()
+        torch.cuda.synchronize()
+        assert not st.any()
+        outs.append((raw.cpu().numpy(), clean.cpu().numpy()))
+    # sub-batching through a minimal workspace changes nothing, bit for bit
+    np.testing.assert_array_equal(outs[0][0], outs[1][0])
+    np.testing.assert_array_equal(outs[0][1], outs[1][1])
+    _assert_feature_parity(outs[0][0][2], ofeat.extract_features(X[2]), "abi raw")
+    # error contract
+    tiny = torch.empty(256, dtype=torch.uint8, device="cuda")
+    rc = lib.dys_features_raw(d_audio.data_ptr(), d_starts.data_ptr(), d_lens.data_ptr(), n, L, raw.data_ptr(),
+                              st.data_ptr(), tiny.data_ptr(), 256, None)
+    assert rc == pkg._lib.ERR_WORKSPACE and b"workspace" in lib.dys_last_error()
+    rc = lib.dys_features_raw(None, d_starts.data_ptr(), d_lens.data_ptr(), n, L, raw.data_ptr(), st.data_ptr(),
+                              tiny.data_ptr(), 256, None)
+    assert rc == pkg._lib.ERR_INVALID
+    rc = lib.dys_features_raw(d_audio.data_ptr(), d_starts.data_ptr(), d_lens.data_ptr(), 0, L, None, None, None, 0, None)
+    assert rc == 0                                            # empty batch is a no-op
+    # lengths outside [0, max_len] are flagged, not read
+    d_bad = torch.tensor([L, L + 1, -5, L, L, L], dtype=torch.int32, device="cuda")
+    ws_bytes = lib.dys_workspace_bytes(n, L, 0)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    st1 = torch.zeros(n, dtype=torch.int32, device="cuda")
+    assert lib.dys_features_raw(d_audio.data_ptr(), d_starts.data_ptr(), d_bad.data_ptr(), n, L, raw.data_ptr(),
+                                st1.data_ptr(), ws.data_ptr(), ws_bytes, None) == 0
+    torch.cuda.synchronize()
+    s = st1.cpu().numpy()
+    assert s[1] & pkg.STATUS_BAD_LENGTH and s[2] & pkg.STATUS_BAD_LENGTH and s[0] == 0
+    assert not raw[1].any() and not raw[2].any()
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at the bench configuration (BASELINE.json configs 2/3: 10 000 clips)
+# ---------------------------------------------------------------------------------------------
+def test_full_size_properties(fe, pkg, synth, torch_cuda):
+    torch = torch_cuda
+    base = synth.synth_batch(50)
+    reps = 200
+    X = torch.from_numpy(base).cuda().repeat(reps, 1)                     # 10 000 x 48 000
+    assert X.shape == (10000, 48000)
+    raw, clean, st = fe.extract_features_batch(X, denoise=True, return_status=True)
+    assert raw.shape == clean.shape == (10000, 149) and not st.any()
+    # (1) a clip's features depend on nothing but the clip: replicas in different sub-batches are bit-identical
+    r = raw.reshape(reps, 50, 149)
+    c = clean.reshape(reps, 50, 149)
+    assert torch.equal(r, r[:1].expand_as(r)) and torch.equal(c, c[:1].expand_as(c))
+    # (2) ... and equal to the small-batch result, which is itself oracle-checked
+    raw_s, clean_s = fe.extract_features_batch(base, denoise=True)
+    assert torch.equal(r[0], raw_s) and torch.equal(c[0], clean_s)
+    for i in (0, 17, 49):
+        _assert_feature_parity(raw_s[i].cpu().numpy(), ofeat.extract_features(base[i]), f"full raw {i}")
+    # (3) raw-only call == raw half of the raw+clean call
+    assert torch.equal(fe.extract_features_batch(X[:4096]), raw[:4096])
+    # (4) sharding: rank shards concatenated in rank order == the single-GPU result
+    parts = []
+    for rank in range(8):
+        lo, hi = pkg.sharding.shard_range(10000, rank, 8)
+        parts.append(fe.extract_features_batch(X[lo:hi]))
+    assert torch.equal(torch.cat(parts), raw)
+    # (5) CMVN: device moments == fp64 host StandardScaler on the same rows; z-scores have mean 0 / var 1
+    sc = pkg.scaler.GlobalScaler().fit(clean)
+    mean, var, scale, n = ocmvn.fit(clean.cpu().numpy())
+    np.testing.assert_allclose(sc.mean_.cpu().numpy(), mean, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(sc.scale_.cpu().numpy(), scale, rtol=1e-9, atol=1e-12)
+    Z = sc.transform(clean).double()
+    assert Z.mean(0).abs().max().item() < 1e-5
+    live = torch.from_numpy(var > 0).cuda()
+    assert (Z.var(0, unbiased=False)[live] - 1).abs().max().item() < 1e-4
+
+
+def test_sliding_windows_need_no_copy(fe, pkg, synth, torch_cuda):
+    """Long-form (BASELINE config 4): overlapping windows addressed in place == the same windows copied out."""
+    torch = torch_cuda
+    rec = np.concatenate([synth.synth_clip(100 + i) for i in range(5)])            # 15 s
+    starts = pkg.sharding.sliding_windows(len(rec))
+    assert len(starts) == 9
+    d = torch.from_numpy(rec).cuda()
+    lens = np.full(len(starts), 48000, np.int32)
+    a_raw, a_clean = fe.extract_features_batch(d, lengths=lens, starts=np.asarray(starts), denoise=True)
+    copies = [rec[s:s + 48000] for s in starts]
+    b_raw, b_clean = fe.extract_features_batch(copies, denoise=True)
+    assert torch.equal(a_raw, b_raw) and torch.equal(a_clean, b_clean)
+    _assert_feature_parity(a_raw[4].cpu().numpy(), ofeat.extract_features(copies[4]), "window 4")
+
+
+def test_host_streaming_path_equals_device_path(fe, synth, torch_cuda):
+    torch = torch_cuda
+    X = torch.from_numpy(synth.synth_batch(40)).pin_memory()
+    h_raw, h_clean = fe.extract_features_host(X, denoise=True, chunk_clips=16)
+    d_raw, d_clean = fe.extract_features_batch(X.cuda(), denoise=True)
+    assert not h_raw.is_cuda and torch.equal(h_raw, d_raw.cpu()) and torch.equal(h_clean, d_clean.cpu())
+    h_only = fe.extract_features_host(X, denoise=False, chunk_clips=7)
+    assert torch.equal(h_only, d_raw.cpu())
+
+
+def test_cache_artifacts_are_reference_compatible(fe, pkg, synth, tmp_path, monkeypatch):
+    """build_feature_cache writes what pipeline1.py:142 / :439 write: PCM-16 WAV + np.save'd float32 (149,)."""
+    monkeypatch.chdir(tmp_path)
+    os.makedirs("in")
+    paths = []
+    for i in range(3):
+        q = owav.quantize_pcm16(synth.synth_clip(30 + i, 20000 + 1000 * i))
+        p = f"in/clip{i}.wav"
+        owav.write_wav_pcm16(p, q)
+        paths.append(p)
+    Xb, Xa, kept = fe.build_feature_cache(paths + ["in/missing.wav"])
+    assert kept == paths and Xb.shape == Xa.shape == (3, 149)
+    for i, p in enumerate(paths):
+        raw = np.load(f"cache_features/clip{i}_raw_feats.npy")
+        clean = np.load(f"cache_features/clip{i}_clean_feats.npy")
+        assert raw.dtype == np.float32 and raw.shape == (149,) and os.path.getsize(f"cache_features/clip{i}_raw_feats.npy") == 724
+        np.testing.assert_array_equal(raw, Xb[i])
+        y, _ = fe.load_audio(p)
+        q_ref = oden.clean_audio(y)
+        q, sr = owav.read_wav_pcm16(f"clear_audio/clip{i}.wav")
+        assert sr == 16000 and np.array_equal(q, q_ref)
+        _assert_feature_parity(clean, ofeat.extract_features(owav.dequantize_pcm16(q_ref)), f"cache clean {i}")
+        # cache hit: the reference-named loader returns the stored vector without touching the GPU
+        np.testing.assert_array_equal(fe.cached_extract_features(p, "", "raw"), raw)
+    assert fe.clean_audio_and_cache(paths[0]) == os.path.normpath("clear_audio/clip0.wav")
