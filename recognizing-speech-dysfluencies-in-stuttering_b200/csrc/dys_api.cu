@@ -34,7 +34,7 @@ int nr_cap() { return env_int("DYS_NR_SUBBATCH", 1024); }
 
 struct Layout {
     int64_t clean_pitch = 0;
-    size_t clean_off = 0, peak_off = 0, flag_off = 0, scratch_off = 0;
+    size_t clean_off = 0, cleanq_off = 0, peak_off = 0, flag_off = 0, scratch_off = 0;
     int t_max = 0, ta_max = 0, cpc = 1;
 };
 
@@ -47,6 +47,7 @@ Layout make_layout(int n_clips, int max_len, bool with_clean) {
     if (with_clean) {
         L.clean_pitch = (int64_t(std::max(max_len, 1)) + 63) & ~int64_t(63);
         L.clean_off = off; off += al256(size_t(n_clips) * L.clean_pitch * 4);
+        L.cleanq_off = off; off += al256(size_t(n_clips) * L.clean_pitch * 2);
         L.peak_off = off; off += al256(size_t(n_clips) * 4);
         L.flag_off = off; off += al256(size_t(n_clips) * 4);
     }
@@ -159,11 +160,12 @@ DYS_API int dys_features_raw_clean(const float* d_audio, const int64_t* d_starts
     }
     unsigned char* ws = static_cast<unsigned char*>(d_workspace);
     float* clean = reinterpret_cast<float*>(ws + L.clean_off);
+    int16_t* clean_q = reinterpret_cast<int16_t*>(ws + L.cleanq_off);
     float* peak = reinterpret_cast<float*>(ws + L.peak_off);
     int32_t* flag = reinterpret_cast<int32_t*>(ws + L.flag_off);
     ClipView cv{};
     cv.audio = d_audio; cv.starts = d_starts; cv.lengths = d_lengths; cv.n_clips = n_clips; cv.max_len = max_len;
-    cv.clean = clean; cv.clean_pitch = L.clean_pitch; cv.clean_peak = peak; cv.clean_flag = flag;
+    cv.clean = clean; cv.clean_pitch = L.clean_pitch; cv.clean_peak = peak; cv.clean_flag = flag; cv.clean_q = clean_q;
 
     // ---- spectral gate over sub-batches of chunks ------------------------------------------
     DYS_CUDA_OK(launch_clean_init(cv, peak, flag, st));
@@ -182,7 +184,7 @@ DYS_API int dys_features_raw_clean(const float* d_audio, const int64_t* d_starts
             DYS_CUDA_OK(launch_denoise(*tb, cv, clean, peak, flag, L.cpc, int(i0), cnt, sc, prop_decrease, st));
         }
     }
-    if (d_clean_pcm) DYS_CUDA_OK(launch_quantize_pcm(cv, d_clean_pcm, d_pcm_starts, st));
+    DYS_CUDA_OK(launch_quantize_pcm(cv, clean_q, d_clean_pcm, d_pcm_starts, st));
     // ---- features of both branches ----------------------------------------------------------
     return run_features(*tb, cv, 2 * n_clips, L, ws, size_t(workspace_bytes), d_out_raw, d_out_clean, d_status, st);
 }

@@ -353,26 +353,33 @@ __global__ void k_clean_init(float* clean_peak, int32_t* clean_flag, const ClipV
     clean_flag[i] = (n <= 0 || n > cv.max_len) ? 1 : 0;        // nothing to clean -> the reference's except branch
 }
 
-// clean float32 -> the int16 PCM the reference writes to clear_audio/<stem>.wav (pipeline1.py:141-142)
-__global__ void k_quantize_pcm(const ClipView cv, int16_t* __restrict__ pcm, const int64_t* __restrict__ pcm_starts) {
+// clean float32 -> the int16 PCM the reference writes to clear_audio/<stem>.wav:
+// librosa.util.normalize (y / max|y|, float32 division) then libsndfile's clip(lrintf(x * 32768))  (pipeline1.py:141-142).
+// The clean feature branch reads clean_q back as int16 / 32768, exactly what librosa.load returns for that WAV.
+__global__ void k_quantize_pcm(const ClipView cv, int16_t* __restrict__ clean_q, int16_t* __restrict__ pcm,
+                               const int64_t* __restrict__ pcm_starts) {
     const int c = blockIdx.x;
     const int n = cv.lengths[c];
     if (n <= 0 || n > cv.max_len) return;
-    int16_t* dst = pcm + pcm_starts[c];
-    if (cv.clean_flag[c] != 0) {           // reference wrote no WAV for this clip; emit the raw samples quantised
+    int16_t* user = pcm ? pcm + pcm_starts[c] : nullptr;
+    if (cv.clean_flag[c] != 0) {           // reference wrote no WAV for this clip; the caller's buffer gets the raw samples quantised
+        if (!user) return;
         const float* src = cv.audio + cv.starts[c];
         for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
             float q = rintf(src[i] * 32768.0f);
-            dst[i] = int16_t(fminf(fmaxf(q, -32768.0f), 32767.0f));
+            user[i] = int16_t(fminf(fmaxf(q, -32768.0f), 32767.0f));
         }
         return;
     }
     float pk = cv.clean_peak[c];
-    if (pk < FLT_MIN) pk = 1.0f;
+    if (pk < FLT_MIN) pk = 1.0f;           // librosa.util.normalize: below tiny -> left unscaled
     const float* src = cv.clean + size_t(c) * cv.clean_pitch;
+    int16_t* dst = clean_q + size_t(c) * cv.clean_pitch;
     for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
         float q = rintf(__fdiv_rn(src[i], pk) * 32768.0f);
-        dst[i] = int16_t(fminf(fmaxf(q, -32768.0f), 32767.0f));
+        const int16_t v = int16_t(fminf(fmaxf(q, -32768.0f), 32767.0f));
+        dst[i] = v;
+        if (user) user[i] = v;
     }
 }
 
@@ -441,11 +448,12 @@ cudaError_t launch_denoise(const DeviceTables& tb, const ClipView& cv, float* cl
     return cudaGetLastError();
 }
 
-cudaError_t launch_quantize_pcm(const ClipView& cv, int16_t* pcm, const int64_t* pcm_starts, cudaStream_t stream) {
+cudaError_t launch_quantize_pcm(const ClipView& cv, int16_t* clean_q, int16_t* pcm, const int64_t* pcm_starts,
+                                cudaStream_t stream) {
     if (cv.n_clips <= 0) return cudaSuccess;
     const int gy = std::max(1, std::min(64, (cv.max_len + 255) / 256));
     LaunchScope ls(kK_quantize_pcm, stream);
-    k_quantize_pcm<<<dim3(cv.n_clips, gy), 256, 0, stream>>>(cv, pcm, pcm_starts);
+    k_quantize_pcm<<<dim3(cv.n_clips, gy), 256, 0, stream>>>(cv, clean_q, pcm, pcm_starts);
     return cudaGetLastError();
 }
 

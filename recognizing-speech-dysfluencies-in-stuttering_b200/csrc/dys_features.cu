@@ -37,20 +37,11 @@ __device__ __forceinline__ int enc_f32(float f) {
 }
 __device__ __forceinline__ float dec_f32(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
-// libsndfile float -> PCM-16 -> librosa.load: clip(lrintf(x * 32768)) / 32768   (pipeline1.py:142, :437)
-__device__ __forceinline__ float pcm16_roundtrip(float y, float peak) {
-    const float s = __fdiv_rn(y, peak) * 32768.0f;
-    float q = rintf(s);
-    q = fminf(fmaxf(q, -32768.0f), 32767.0f);
-    return q * (1.0f / 32768.0f);
-}
-
 struct InstSrc {
-    const float* base;   // first sample of the clip on this branch
+    const float* f32;    // float32 samples of the clip on this branch (raw clip, or raw clip as clean fallback) ...
+    const int16_t* q16;  // ... or the PCM-16 the reference would have written to clear_audio/<stem>.wav (clean branch)
     int n;               // samples
-    float peak;          // > 0: apply normalise + PCM-16 round trip with this divisor; 0: plain samples
-    bool vec_ok;         // base is 8-byte aligned
-    bool check_finite;
+    bool vec_ok;         // f32 is 8-byte aligned
 };
 
 __device__ __forceinline__ InstSrc inst_source(const ClipView& cv, int inst) {
@@ -60,17 +51,10 @@ __device__ __forceinline__ InstSrc inst_source(const ClipView& cv, int inst) {
     int n = cv.lengths[c];
     if (n < 0 || n > cv.max_len) n = 0;
     s.n = n;
-    s.peak = 0.f;
-    s.check_finite = true;
-    s.base = cv.audio + cv.starts[c];
-    if (clean && cv.clean_flag[c] == 0) {
-        s.base = cv.clean + int64_t(c) * cv.clean_pitch;
-        float pk = cv.clean_peak[c];
-        if (pk < FLT_MIN) pk = 1.0f;             // librosa.util.normalize: below tiny -> left unscaled
-        s.peak = pk;
-        s.check_finite = false;
-    }
-    s.vec_ok = (reinterpret_cast<uintptr_t>(s.base) & 7u) == 0;
+    s.f32 = cv.audio + cv.starts[c];
+    s.q16 = nullptr;
+    if (clean && cv.clean_flag[c] == 0) s.q16 = cv.clean_q + int64_t(c) * cv.clean_pitch;
+    s.vec_ok = (reinterpret_cast<uintptr_t>(s.f32) & 7u) == 0;
     return s;
 }
 
@@ -92,6 +76,13 @@ __global__ void k_feat_init(int* peak_count, int* lmax_enc, int32_t* status, con
 }
 
 // ------------------------------------------------------------------------------------------
+// Per-warp scratch inside the 32x33 float2 exchange tile (8448 B), reused along the frame:
+//   [0, 8192)      windowed frame as 1024 complex pairs (before the FFT)
+//   [0, 8448)      transposition tile (during the FFT)
+//   [0, 4100)      power spectrum P[0..1024]           (after the FFT)
+//   [4224, 8328)   upper half of the complex spectrum: zb[j] = Z[512 + j], j = 1..511, zb[512] = Z[0]
+constexpr int kZbOffset = 528;             // in float2 units
+
 struct SpectraSmem {
     float hann[kNfft];
     float2 tw[32 * 32];
@@ -125,70 +116,99 @@ k_frame_spectra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
     __syncthreads();
 
     float2* xbuf = sm.xbuf[warp];
-    float* pbuf = reinterpret_cast<float*>(xbuf);          // the warp's 1025-bin power spectrum (aliases the tile)
+    float* pbuf = reinterpret_cast<float*>(xbuf);
+    float2* zb = xbuf + kZbOffset;
+    const float2* hann2 = reinterpret_cast<const float2*>(sm.hann);
     float* g_power = sc.power + size_t(li) * sc.t_max * kBinsPad;
     float* g_logmel = sc.logmel + size_t(li) * sc.t_max * kMels;
     float2* g_peaks = sc.peaks + size_t(li) * sc.t_max * kMaxPeaksPerFrame;
     float warp_lmax = -INFINITY;
     bool nonfinite = false;
+    const int n = src.n;
 
     for (int t = t_begin + warp; t < t_end; t += kWarps) {
-        // ---- load + window: z[j] = (x[2j], x[2j+1]) * hann, j = lane + 32 m ------------------
-        float2 v[32];
+        // ---- stage the windowed frame: xs[i] = (x[2i], x[2i+1]) * hann, zero centre padding -----
         const int f0 = t * kHop - kNfft / 2;               // clip-relative index of the frame's first sample
+        const bool interior = f0 >= 0 && f0 + kNfft <= n;
+        if (src.q16) {                                      // clean branch: int16 / 32768 (exact), as librosa.load reads the WAV
+            const int16_t* q = src.q16;
+#pragma unroll 4
+            for (int i = lane; i < kNfft / 2; i += 32) {
+                const int s = f0 + 2 * i;
+                float a = 0.f, b = 0.f;
+                if (interior) {
+                    const short2 p = __ldg(reinterpret_cast<const short2*>(q + s));
+                    a = float(p.x); b = float(p.y);
+                } else {
+                    if (s >= 0 && s < n) a = float(__ldg(q + s));
+                    if (s + 1 >= 0 && s + 1 < n) b = float(__ldg(q + s + 1));
+                }
+                const float2 w = hann2[i];
+                xbuf[i] = make_float2(a * (1.0f / 32768.0f) * w.x, b * (1.0f / 32768.0f) * w.y);
+            }
+        } else {
+            const float* x = src.f32;
+            const bool vec = interior && src.vec_ok;
+#pragma unroll 4
+            for (int i = lane; i < kNfft / 2; i += 32) {
+                const int s = f0 + 2 * i;
+                float a = 0.f, b = 0.f;
+                if (vec) {
+                    const float2 p = __ldg(reinterpret_cast<const float2*>(x + s));
+                    a = p.x; b = p.y;
+                } else {
+                    if (s >= 0 && s < n) a = __ldg(x + s);
+                    if (s + 1 >= 0 && s + 1 < n) b = __ldg(x + s + 1);
+                }
+                nonfinite |= !(isfinite(a) && isfinite(b));
+                const float2 w = hann2[i];
+                xbuf[i] = make_float2(a * w.x, b * w.y);
+            }
+        }
+        __syncwarp();
+        float2 v[32];
         static_for<32>([&](auto im) {
             constexpr int m = decltype(im)::value;
-            const int j2 = 2 * (lane + 32 * m);
-            const int s = f0 + j2;
-            float a = 0.f, b = 0.f;
-            if (s >= 0 && s + 1 < src.n && src.vec_ok) {
-                const float2 p = __ldg(reinterpret_cast<const float2*>(src.base + s));
-                a = p.x; b = p.y;
-            } else {
-                if (s >= 0 && s < src.n) a = __ldg(src.base + s);
-                if (s + 1 >= 0 && s + 1 < src.n) b = __ldg(src.base + s + 1);
-            }
-            if (src.peak > 0.f) {
-                a = (s >= 0 && s < src.n) ? pcm16_roundtrip(a, src.peak) : 0.f;
-                b = (s + 1 >= 0 && s + 1 < src.n) ? pcm16_roundtrip(b, src.peak) : 0.f;
-            } else if (src.check_finite) {
-                nonfinite |= !(isfinite(a) && isfinite(b));
-            }
-            const float2 w = *reinterpret_cast<const float2*>(&sm.hann[j2]);
-            v[m] = make_float2(a * w.x, b * w.y);
+            v[m] = xbuf[lane + 32 * m];
         });
+        __syncwarp();
 
-        warp_fft1024(v, xbuf, sm.tw, lane);
+        warp_fft1024_rolled(v, xbuf, sm.tw, lane);          // Z[lane + 32 q] = v[bitrev(q)]
 
-        // ---- real split -> power spectrum P[k], k = lane + 32 q --------------------------------
-        // X[k] = (Z[k] + conj Z[1024-k]) / 2 - i e^{-2 pi i k / 2048} (Z[k] - conj Z[1024-k]) / 2 ;
-        // Z[1024-k] sits in lane (32 - lane) & 31, register 31 - q (lane 0: its own register (32 - q) & 31).
-        // The exchange tile is dead after the transposition, so P is written straight into it.
+        // ---- real split, two bins per pair: with E = (Z[k] + conj Z[1024-k]) / 2 and
+        // T = e^{-2 pi i k / 2048} * (-i) (Z[k] - conj Z[1024-k]) / 2 :  X[k] = E + T,  X[1024-k] = conj(E - T).
+        // k = 0 pairs with the Nyquist bin through zb[512] = Z[0]; k = 512 is its own partner.
+        static_for<16>([&](auto iq) {
+            constexpr int q = decltype(iq)::value + 16;
+            zb[lane + 32 * (q - 16)] = v[bitrev(q, 5)];     // Z[512 + lane + 32 (q - 16)]
+        });
+        if (lane == 0) zb[512] = v[0];
+        __syncwarp();
         float* gp = g_power + size_t(t) * kBinsPad;
-        const int src_lane = (32 - lane) & 31;
         float fmax_ = 0.f;
-        static_for<32>([&](auto iq) {
+        static_for<16>([&](auto iq) {
             constexpr int q = decltype(iq)::value;
-            const int k = lane + 32 * q;
-            const float2 z = v[q];
-            float2 p;
-            p.x = __shfl_sync(0xffffffffu, v[31 - q].x, src_lane);
-            p.y = __shfl_sync(0xffffffffu, v[31 - q].y, src_lane);
-            if (lane == 0) p = v[(32 - q) & 31];
+            const int k = lane + 32 * q;                    // 0 .. 511
+            const float2 z = v[bitrev(q, 5)];
+            const float2 p = zb[512 - k];                   // Z[1024 - k]  (k = 0: Z[0])
             const float ex = z.x + p.x, ey = z.y - p.y, dx = z.x - p.x, dy = z.y + p.y;
             const float2 cs = sm.split[k];
-            const float xr = ex + (cs.x * dy - cs.y * dx);
-            const float xi = ey - (cs.x * dx + cs.y * dy);
-            const float pw = 0.25f * (xr * xr + xi * xi);
-            fmax_ = fmaxf(fmax_, pw);
-            pbuf[k] = pw;
-            gp[k] = pw;
+            const float tx = cs.x * dy - cs.y * dx, ty = -(cs.x * dx + cs.y * dy);
+            const float ar = ex + tx, ai = ey + ty, br = ex - tx, bi = ey - ty;
+            const float plo = 0.25f * (ar * ar + ai * ai);
+            const float phi = 0.25f * (br * br + bi * bi);
+            fmax_ = fmaxf(fmax_, fmaxf(plo, phi));
+            gp[k] = plo;
+            gp[1024 - k] = phi;
+            pbuf[k] = plo;                                  // the power row lives below the zb region of the tile
+            pbuf[1024 - k] = phi;
         });
-        {
-            const float z0x = __shfl_sync(0xffffffffu, v[0].x, 0), z0y = __shfl_sync(0xffffffffu, v[0].y, 0);
-            const float p_nyq = (z0x - z0y) * (z0x - z0y);
-            fmax_ = fmaxf(fmax_, p_nyq);
-            if (lane == 0) { pbuf[1024] = p_nyq; gp[1024] = p_nyq; }
+        if (lane == 0) {
+            const float2 z = v[bitrev(16, 5)];
+            const float p_mid = z.x * z.x + z.y * z.y;      // X[512] = conj Z[512]
+            gp[512] = p_mid;
+            pbuf[512] = p_mid;
+            fmax_ = fmaxf(fmax_, p_mid);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) fmax_ = fmaxf(fmax_, __shfl_xor_sync(0xffffffffu, fmax_, o));
@@ -196,11 +216,12 @@ k_frame_spectra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
 
         // ---- sparse slaney mel (<= 2 filters per bin) + 10 log10 ---------------------------------
         float* gl = g_logmel + size_t(t) * kMels;
-#pragma unroll
+#pragma unroll 1
         for (int g = 0; g < 4; ++g) {
             const int f = lane + 32 * g;
             const int st = sm.mel_start[f], ln = sm.mel_len[f], pt = sm.mel_ptr[f];
             float acc = 0.f;
+#pragma unroll 4
             for (int j = 0; j < ln; ++j) acc = fmaf(sm.mel_w[pt + j], pbuf[st + j], acc);
             const float L = 10.0f * log10f(fmaxf(acc, 1e-10f));
             gl[f] = L;
@@ -210,7 +231,7 @@ k_frame_spectra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
         // ---- piptrack: thresholded local maxima in [150, 4000) Hz, parabolic refinement ----------
         const float ref = 0.1f * fmax_;
         unsigned pkmask = 0;
-#pragma unroll
+#pragma unroll 4
         for (int q = 0; q < 16; ++q) {
             const int k = lane + 32 * q;
             if (k >= kPipLo) {

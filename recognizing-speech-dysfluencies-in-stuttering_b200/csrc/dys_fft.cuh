@@ -132,6 +132,31 @@ __device__ __forceinline__ void warp_fft1024(float2 (&v)[32], float2* xbuf, cons
     static_for<32>([&](auto iq) { constexpr int q = decltype(iq)::value; v[q] = o[q]; });
 }
 
+// Compact-code variant: the two 32-point register passes share ONE copy of the butterfly code
+// (a 2-trip rolled loop), which keeps the frame loop inside the instruction cache.  The result
+// is left bit-reversed:  Z[lane + 32 q] = v[bitrev(q, 5)]  (static renaming is free).
+__device__ __forceinline__ void warp_fft1024_rolled(float2 (&v)[32], float2* xbuf, const float2* __restrict__ tw, int lane) {
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        fft_reg<32, float>(v);
+        if (pass == 0) {
+            static_for<32>([&](auto ik) {
+                constexpr int kA = decltype(ik)::value;
+                constexpr int r = bitrev(kA, 5);
+                float2 val = v[r];
+                if constexpr (kA != 0) val = cmul(val, tw[kA * 32 + lane]);
+                xbuf[lane * 33 + kA] = val;
+            });
+            __syncwarp();
+            static_for<32>([&](auto il) {
+                constexpr int l = decltype(il)::value;
+                v[l] = xbuf[l * 33 + lane];
+            });
+            __syncwarp();
+        }
+    }
+}
+
 // ---- 512-point complex FFT, fp64, one warp -------------------------------------------------
 // in : v[m] = z[lane + 32 m], m < 16   out: v[q] = Z[lane + 32 q], q < 16
 // xbuf: 16x33 double2 private to the warp; tw512[kA*32 + l] = W_512^(l*kA);

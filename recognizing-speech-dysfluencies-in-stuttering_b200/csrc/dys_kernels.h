@@ -28,6 +28,7 @@ struct ClipView {
     const float* clean;          // [n_clips][clean_pitch] denoised float32, before normalise/quantise
     int64_t clean_pitch;
     const float* clean_peak;     // [n_clips] max |clean|
+    const int16_t* clean_q;      // [n_clips][clean_pitch] PCM-16 of the normalised clean clip (what sf.write stores)
     const int32_t* clean_flag;   // [n_clips] non-zero -> fall back to the raw samples
 };
 
@@ -69,7 +70,10 @@ cudaError_t launch_denoise(const DeviceTables& tb, const ClipView& cv, float* cl
                            int chunks_per_clip, int item0, int n_items, const NrScratch& sc, float prop_decrease,
                            cudaStream_t stream);
 cudaError_t launch_clean_init(const ClipView& cv, float* clean_peak, int32_t* clean_flag, cudaStream_t stream);
-cudaError_t launch_quantize_pcm(const ClipView& cv, int16_t* pcm, const int64_t* pcm_starts, cudaStream_t stream);
+// clean float32 -> PCM-16: always into clean_q (workspace, read by the clean feature branch), and into the caller's
+// packed buffer when pcm != nullptr.
+cudaError_t launch_quantize_pcm(const ClipView& cv, int16_t* clean_q, int16_t* pcm, const int64_t* pcm_starts,
+                                cudaStream_t stream);
 
 // CMVN: acc[0] = n, acc[1..149] = sum (x - shift), acc[150..298] = sum (x - shift)^2
 // (float64, fixed summation order -> bit-reproducible); shift may be null (= 0).
