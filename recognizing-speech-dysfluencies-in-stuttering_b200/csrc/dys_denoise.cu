@@ -9,13 +9,16 @@
 // float64; so do these kernels, because the PCM-16 quantiser that follows (pipeline1.py:142)
 // turns float32-level errors into LSB flips.
 //
-//   k_nr_stft_mag    : one warp per frame, 512-point complex fp64 FFT  -> |D|           [frames x 513]
-//   k_nr_iir_mask    : one thread per (chunk, bin): forward IIR, closed-form zero tail, backward IIR,
-//                      sigmoid -> raw mask (in place); NaN (0/0) raises the clip's fallback flag
-//   k_nr_smooth      : 7-tap time then 33-tap frequency triangular smoothing, prop_decrease blend
-//   k_nr_apply_istft : one warp per frame: FFT again, * mask, inverse FFT, synthesis window
-//   k_nr_overlap_add : one thread per output sample: 4-frame overlap-add (ascending frame order),
-//                      / window-sum-square, cast to float32, clip peak via atomicMax
+//   k_nr_stft_mag  : one warp per frame, 512-point complex fp64 FFT  -> |D|            [frames x 513]
+//   k_nr_iir_mask  : one thread per (chunk, bin), sequential in time: forward IIR (only check-points
+//                    kept), closed-form zero tail, backward IIR with the forward state re-derived in
+//                    reverse, sigmoid, and the 7-tap time smoothing of the mask through a register
+//                    window -> time-smoothed mask, in place.  NaN (0/0) raises the clip's fallback flag
+//   k_nr_apply_ola : one warp per frame: FFT again, 33-tap frequency smoothing of the mask row
+//                    (register-tiled, taps in constant memory), * mask, inverse FFT, synthesis window;
+//                    the CTA overlap-adds its frames in shared memory (ascending frame order, like
+//                    librosa's __overlap_add), divides by the window-sum-square, stores float32 and
+//                    maxes the clip peak.  Inverse frames never touch HBM.
 // Only frames that overlap the un-padded samples are touched (191 of 422 for a 3-s clip).
 #include <algorithm>
 #include <cfloat>
@@ -32,6 +35,8 @@ namespace {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kFramesPerCta = 64;
+
+__constant__ double c_smooth_f[kNrFreqTaps];      // noisereduce's frequency smoothing taps (sum 1)
 
 struct NrGeom {
     int clip, n, c0, out_len, L, Tn, t_first, t_last;
@@ -67,23 +72,22 @@ __device__ __forceinline__ NrGeom nr_geom(const ClipView& cv, int item, int cpc)
     return g;
 }
 
-struct NrSmem {
+struct NrTables {
     double hann[kNrFft];
     double2 tw512[16 * 32];
     double2 tw32h[32];
     double2 split[512];
-    double2 xbuf[kWarps][kXbuf512];
 };
 
-__device__ __forceinline__ void nr_load_tables(NrSmem& sm, const DeviceTables& tb, int tid) {
-    for (int i = tid; i < kNrFft; i += kThreads) sm.hann[i] = tb.hann1024[i];
-    for (int i = tid; i < 512; i += kThreads) { sm.tw512[i] = tb.tw512[i]; sm.split[i] = tb.split1024[i]; }
+__device__ __forceinline__ void nr_load_tables(NrTables& sm, const DeviceTables& tb, int tid, int nthreads) {
+    for (int i = tid; i < kNrFft; i += nthreads) sm.hann[i] = tb.hann1024[i];
+    for (int i = tid; i < 512; i += nthreads) { sm.tw512[i] = tb.tw512[i]; sm.split[i] = tb.split1024[i]; }
     if (tid < 32) sm.tw32h[tid] = tb.tw32h[tid];
 }
 
 // Windowed frame t of the zero-padded chunk -> STFT bins.  On return x[q] = D[lane + 32 q] (q < 16)
 // and *nyq = D[512] (real).
-__device__ __forceinline__ void nr_frame_stft(const NrSmem& sm, double2* xbuf, const float* __restrict__ base, bool vec_ok,
+__device__ __forceinline__ void nr_frame_stft(const NrTables& sm, double2* xbuf, const float* __restrict__ base, bool vec_ok,
                                               const NrGeom& g, int t, int lane, double2 (&x)[16], double* nyq) {
     double2 v[16];
     const int p0 = t * kNrHop - kNrFft / 2;                 // padded-chunk coordinate of the frame's first sample
@@ -104,16 +108,17 @@ __device__ __forceinline__ void nr_frame_stft(const NrSmem& sm, double2* xbuf, c
         }
         v[m] = make_double2(double(a) * sm.hann[j2], double(b) * sm.hann[j2 + 1]);
     });
-    warp_fft512(v, xbuf, sm.tw512, sm.tw32h, lane);
+    warp_fft512_rolled(v, xbuf, sm.tw512, sm.tw32h, lane);  // Z[lane + 32 q] = v[bitrev(q, 4)]
     const int src_lane = (32 - lane) & 31;
     static_for<16>([&](auto iq) {
         constexpr int q = decltype(iq)::value;
+        constexpr int rq = bitrev(q, 4), rp = bitrev(15 - q, 4), r0 = bitrev((16 - q) & 15, 4);
         const int k = lane + 32 * q;
-        const double2 z = v[q];
+        const double2 z = v[rq];
         double2 p;
-        p.x = __shfl_sync(0xffffffffu, v[15 - q].x, src_lane);
-        p.y = __shfl_sync(0xffffffffu, v[15 - q].y, src_lane);
-        if (lane == 0) p = v[(16 - q) & 15];
+        p.x = __shfl_sync(0xffffffffu, v[rp].x, src_lane);
+        p.y = __shfl_sync(0xffffffffu, v[rp].y, src_lane);
+        if (lane == 0) p = v[r0];
         const double ex = z.x + p.x, ey = z.y - p.y, dx = z.x - p.x, dy = z.y + p.y;
         const double2 cs = sm.split[k];
         x[q] = make_double2(0.5 * (ex + (cs.x * dy - cs.y * dx)), 0.5 * (ey - (cs.x * dx + cs.y * dy)));
@@ -123,17 +128,22 @@ __device__ __forceinline__ void nr_frame_stft(const NrSmem& sm, double2* xbuf, c
 }
 
 // ------------------------------------------------------------------------------------------
+struct MagSmem {
+    NrTables tab;
+    double2 xbuf[kWarps][kXbuf512];
+};
+
 __global__ void __launch_bounds__(kThreads, 2)
 k_nr_stft_mag(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrScratch sc) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    NrSmem& sm = *reinterpret_cast<NrSmem*>(smem_raw);
+    MagSmem& sm = *reinterpret_cast<MagSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int li = blockIdx.x;
     const NrGeom g = nr_geom(cv, item0 + li, cpc);
     const int t_begin = g.t_first + blockIdx.y * kFramesPerCta;
     if (t_begin > g.t_last) return;
     const int t_end = min(g.t_last + 1, t_begin + kFramesPerCta);
-    nr_load_tables(sm, tb, tid);
+    nr_load_tables(sm.tab, tb, tid, kThreads);
     __syncthreads();
     const float* base = cv.audio + cv.starts[g.clip];
     const bool vec_ok = (reinterpret_cast<uintptr_t>(base) & 7u) == 0 && (g.c0 & 1) == 0;
@@ -141,7 +151,7 @@ k_nr_stft_mag(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
     for (int t = t_begin + warp; t < t_end; t += kWarps) {
         double2 x[16];
         double nyq;
-        nr_frame_stft(sm, sm.xbuf[warp], base, vec_ok, g, t, lane, x, &nyq);
+        nr_frame_stft(sm.tab, sm.xbuf[warp], base, vec_ok, g, t, lane, x, &nyq);
         double* row = mag + size_t(t - g.t_first) * kNrBinsPad;
         static_for<16>([&](auto iq) {
             constexpr int q = decltype(iq)::value;
@@ -153,21 +163,36 @@ k_nr_stft_mag(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
 }
 
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
+// filtfilt([b], [1, b - 1]) over time + sigmoid + 7-tap time smoothing, one thread per bin.
+constexpr int kIirThreads = 32;
+constexpr int kIirCkShift = 7;                       // forward state check-pointed every 128 frames
+constexpr int kIirMaxCk = 24;                        // covers ta_max <= 3072 (a full 660 000-sample chunk has 2579)
+
+__global__ void __launch_bounds__(kIirThreads)
 k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrScratch sc, int32_t* __restrict__ clean_flag) {
+    __shared__ double ck[kIirMaxCk][kIirThreads];
     const int li = blockIdx.x;
-    const int k = blockIdx.y * 128 + threadIdx.x;
+    const int k = blockIdx.y * kIirThreads + threadIdx.x;
     const NrGeom g = nr_geom(cv, item0 + li, cpc);
     if (k >= kNrBins || g.t_last < g.t_first) return;
     const int Ta = g.t_last - g.t_first + 1;
-    double* mag = sc.mag + size_t(li) * sc.ta_max * kNrBinsPad + k;
-    double* fwd = sc.fwd + size_t(li) * sc.ta_max * kNrBinsPad + k;
-    const double b = tb.iir_b, r = 1.0 - b;
+    constexpr size_t P = kNrBinsPad;
+    double* col = sc.mag + size_t(li) * sc.ta_max * P + k;
+    const double b = tb.iir_b, r = 1.0 - b, rinv = 1.0 / r;
     // forward: f[t] = b A[t] + (1 - b) f[t-1],  f[-1] := A[0]  (lfilter_zi steady state; A[0] = 0 when padded)
-    double prev = (g.t_first == 0) ? mag[0] : 0.0;
-    for (int i = 0; i < Ta; ++i) {
-        prev = b * mag[size_t(i) * kNrBinsPad] + r * prev;
-        fwd[size_t(i) * kNrBinsPad] = prev;
+    double prev = (g.t_first == 0) ? col[0] : 0.0;
+    int i = 0;
+    for (; i + 8 <= Ta; i += 8) {
+        double a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = col[size_t(i + u) * P];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) prev = b * a[u] + r * prev;
+        if (((i + 8) & ((1 << kIirCkShift) - 1)) == 0) ck[((i + 8) >> kIirCkShift) - 1][threadIdx.x] = prev;
+    }
+    for (; i < Ta; ++i) {
+        prev = b * col[size_t(i) * P] + r * prev;
+        if (((i + 1) & ((1 << kIirCkShift) - 1)) == 0) ck[i >> kIirCkShift][threadIdx.x] = prev;
     }
     // frames t_last+1 .. Tn-1 hold zeros: f decays geometrically and the backward recursion over them,
     // started from S[Tn] := f[Tn-1], collapses to  S[t_last+1] = r F u,  u <- b + r^2 u  (m-1 times from 1).
@@ -175,175 +200,228 @@ k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
     double nxt = prev;
     if (m > 0) {
         double u = 1.0;
-        for (int i = 1; i < m; ++i) u = b + r * r * u;
+        for (int j = 1; j < m; ++j) u = b + r * r * u;
         nxt = r * prev * u;
     }
+    // frames outside the active range but inside [0, Tn) hold |D| = 0 over a positive floor: the raw mask
+    // there is exactly sigmoid(-30); outside [0, Tn) the 'same' convolution pads zeros.
+    const double c_pad = 1.0 / (1.0 + exp(30.0));
+    auto virt = [&](int rsrc) { const int t = g.t_first + rsrc; return (t >= 0 && t < g.Tn) ? c_pad : 0.0; };
+    double ft[kNrTimeTaps];
+#pragma unroll
+    for (int j = 0; j < kNrTimeTaps; ++j) ft[j] = tb.smooth_t[j];
+    double w[kNrTimeTaps];                            // w[j] = raw mask of row i + j
+#pragma unroll
+    for (int j = 0; j < kNrTimeTaps - 1; ++j) w[j] = virt(Ta + j);
+    w[kNrTimeTaps - 1] = 0.0;
+    double fcur = prev;                               // f[Ta-1]
     bool bad = false;
-    for (int i = Ta - 1; i >= 0; --i) {
-        const double S = b * fwd[size_t(i) * kNrBinsPad] + r * nxt;
-        nxt = S;
-        const double A = mag[size_t(i) * kNrBinsPad];
-        const double above = (A - S) / S;
-        const double m0 = 1.0 / (1.0 + exp(-(above + -2.0) * 10.0));
-        bad |= isnan(m0);
-        mag[size_t(i) * kNrBinsPad] = m0;
+    // backward: S[t] = b f[t] + (1 - b) S[t+1]; the forward state is re-derived as f[t-1] = (f[t] - b A[t]) / (1 - b)
+    // (error growth (1/r)^128 = 2.8 between check-points); row i+3 of the time-smoothed mask is complete once
+    // the raw mask of row i is known, and overwrites |D| in place (row i+3 was consumed three steps earlier).
+    for (i = Ta - 1; i >= -3; --i) {
+        double m0;
+        if (i >= 0) {
+            const double A = col[size_t(i) * P];
+            const double S = b * fcur + r * nxt;
+            nxt = S;
+            const double above = (A - S) / S;
+            m0 = 1.0 / (1.0 + exp(-(above + -2.0) * 10.0));
+            bad |= isnan(m0);
+            if (i > 0) {
+                if ((i & ((1 << kIirCkShift) - 1)) == 0) fcur = ck[(i >> kIirCkShift) - 1][threadIdx.x];
+                else fcur = (fcur - b * A) * rinv;
+            }
+        } else {
+            m0 = virt(i);
+        }
+#pragma unroll
+        for (int j = kNrTimeTaps - 1; j > 0; --j) w[j] = w[j - 1];
+        w[0] = m0;
+        const int row = i + 3;
+        if (row < Ta) {
+            double acc = 0.0;
+#pragma unroll
+            for (int bb = 0; bb < kNrTimeTaps; ++bb) acc += ft[bb] * w[kNrTimeTaps - 1 - bb];
+            col[size_t(row) * P] = acc;
+        }
     }
     if (bad) atomicOr(&clean_flag[g.clip], 1);
 }
 
 // ------------------------------------------------------------------------------------------
-constexpr int kSmoothRows = 8;
-constexpr int kSmoothPitch = kNrBins + 32;      // 16 zero bins either side ('same' convolution)
+// Mask row layout in shared memory: bin k (-16 <= k <= 528) at index k + floor(k / 16) + 17, i.e. one
+// pad slot per 16 bins, so that lanes reading 16-bin segments at stride 17 doubles do not collide.
+__device__ __forceinline__ int mrow_idx(int k) { return k + (k >> 4) + 17; }
 
-__global__ void __launch_bounds__(kThreads)
-k_nr_smooth(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrScratch sc, double prop) {
-    __shared__ double rows[kSmoothRows][kSmoothPitch];
-    __shared__ double ff[kNrFreqTaps], ft[kNrTimeTaps];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int li = blockIdx.x;
-    const NrGeom g = nr_geom(cv, item0 + li, cpc);
-    const int Ta = g.t_last - g.t_first + 1;
-    const int r_begin = blockIdx.y * kSmoothRows;
-    if (r_begin >= Ta) return;
-    if (tid < kNrFreqTaps) ff[tid] = tb.smooth_f[tid];
-    if (tid < kNrTimeTaps) ft[tid] = tb.smooth_t[tid];
-    __syncthreads();
-    const double* m0 = sc.mag + size_t(li) * sc.ta_max * kNrBinsPad;
-    double* out = sc.fwd + size_t(li) * sc.ta_max * kNrBinsPad;
-    // frames outside the active range but inside [0, Tn) hold |D| = 0 over a positive floor: the raw
-    // mask there is exactly sigmoid(-30); outside [0, Tn) the 'same' convolution pads zeros.
-    const double c_pad = 1.0 / (1.0 + exp(30.0));
-    for (int i = tid; i < kSmoothRows * kSmoothPitch; i += kThreads) {
-        const int rr = i / kSmoothPitch, col = i - rr * kSmoothPitch;
-        const int k = col - 16;
-        const int row = r_begin + rr;
-        double acc = 0.0;
-        if (k >= 0 && k < kNrBins && row < Ta) {
-#pragma unroll
-            for (int bb = 0; bb < kNrTimeTaps; ++bb) {
-                const int rsrc = row + 3 - bb;
-                const int t = g.t_first + rsrc;
-                double v;
-                if (rsrc >= 0 && rsrc < Ta) v = m0[size_t(rsrc) * kNrBinsPad + k];
-                else v = (t >= 0 && t < g.Tn) ? c_pad : 0.0;
-                acc += ft[bb] * v;
-            }
-        }
-        rows[rr][col] = acc;
-    }
-    __syncthreads();
-    const int row = r_begin + warp;
-    if (row < Ta) {
-        for (int k = lane; k < kNrBins; k += 32) {
-            double acc = 0.0;
-#pragma unroll
-            for (int a = 0; a < kNrFreqTaps; ++a) acc += ff[a] * rows[warp][k + 32 - a];
-            out[size_t(row) * kNrBinsPad + k] = acc * prop + (1.0 - prop);
-        }
-    }
-}
+template <int W>
+struct ApplySmem {
+    NrTables tab;
+    double wss[kNrHop];
+    double carry[2][3][kNrHop];
+    float red[W];
+    int bad;
+    double2 xbuf[W][kXbuf512];
+};
 
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1)
-k_nr_apply_istft(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrScratch sc) {
+template <int W>
+__global__ void __launch_bounds__(W * 32, 1)
+k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrScratch sc, double prop, int blocks_per_cta,
+               float* __restrict__ clean, float* __restrict__ clean_peak, int32_t* __restrict__ clean_flag) {
+    constexpr int kT = W * 32;
+    constexpr int kGroups = kT / kNrHop;               // thread groups of 256 for the overlap-add
+    static_assert(kT % kNrHop == 0 && W % kGroups == 0, "overlap-add needs whole groups of 256 threads");
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    NrSmem& sm = *reinterpret_cast<NrSmem*>(smem_raw);
+    ApplySmem<W>& sm = *reinterpret_cast<ApplySmem<W>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int li = blockIdx.x;
     const NrGeom g = nr_geom(cv, item0 + li, cpc);
-    const int t_begin = g.t_first + blockIdx.y * kFramesPerCta;
-    if (t_begin > g.t_last) return;
-    const int t_end = min(g.t_last + 1, t_begin + kFramesPerCta);
-    nr_load_tables(sm, tb, tid);
+    if (g.out_len <= 0) return;
+    // output blocks of 256 samples in padded-chunk coordinates: block h = [256 h, 256 h + 256)
+    const int h_first = kNrPad / kNrHop, h_last = (kNrPad + g.out_len - 1) / kNrHop;
+    const int hb = h_first + blockIdx.y * blocks_per_cta;
+    if (hb > h_last) return;
+    const int he = min(h_last + 1, hb + blocks_per_cta);      // exclusive
+    nr_load_tables(sm.tab, tb, tid, kT);
+    for (int i = tid; i < kNrHop; i += kT) sm.wss[i] = tb.wss[i];
+    if (tid == 0) sm.bad = 0;
     __syncthreads();
     const float* base = cv.audio + cv.starts[g.clip];
     const bool vec_ok = (reinterpret_cast<uintptr_t>(base) & 7u) == 0 && (g.c0 & 1) == 0;
-    const double* mask = sc.fwd + size_t(li) * sc.ta_max * kNrBinsPad;
-    double* frames = sc.frames + size_t(li) * sc.ta_max * kNrFft;
+    const double* tsm = sc.mag + size_t(li) * sc.ta_max * kNrBinsPad;
+    float* out = clean + size_t(g.clip) * cv.clean_pitch + g.c0;
+    double2* xb = sm.xbuf[warp];
+    double* mrow = reinterpret_cast<double*>(xb);
     const int src_lane = (32 - lane) & 31;
-    for (int t = t_begin + warp; t < t_end; t += kWarps) {
-        double2 x[16];
-        double nyq;
-        nr_frame_stft(sm, sm.xbuf[warp], base, vec_ok, g, t, lane, x, &nyq);
-        const double* mrow = mask + size_t(t - g.t_first) * kNrBinsPad;
-        static_for<16>([&](auto iq) {
-            constexpr int q = decltype(iq)::value;
-            const double mk_ = mrow[lane + 32 * q];
-            x[q].x *= mk_; x[q].y *= mk_;
-        });
-        nyq *= mrow[512];
-        // inverse real split: Z'[k] = (X[k] + conj X[512-k]) + i e^{+2 pi i k/1024} (X[k] - conj X[512-k]);
-        // the inverse FFT is taken as conj(FFT(conj Z')), overall scale 1/1024.
-        double2 v[16];
-        static_for<16>([&](auto iq) {
-            constexpr int q = decltype(iq)::value;
-            const int k = lane + 32 * q;
-            const double2 a = x[q];
-            double2 p;
-            p.x = __shfl_sync(0xffffffffu, x[15 - q].x, src_lane);
-            p.y = __shfl_sync(0xffffffffu, x[15 - q].y, src_lane);
-            if (lane == 0) {
-                if constexpr (q == 0) p = make_double2(nyq, 0.0);
-                else p = x[16 - q];
+    const double one_minus_prop = 1.0 - prop;
+    float peak = 0.f;
+    bool bad = false;
+    int cbuf = 0;
+
+    // block h is the sum of frames h-1 .. h+2: frames hb-1 .. he+1 are needed
+    for (int T0 = hb - 1; T0 - 2 < he; T0 += W) {
+        const int t = T0 + warp;
+        if (t >= g.t_first && t <= g.t_last && t <= he + 1) {
+            double2 x[16];
+            double nyq;
+            nr_frame_stft(sm.tab, xb, base, vec_ok, g, t, lane, x, &nyq);
+            // ---- time-smoothed mask row -> shared (zero halo: 'same' convolution) ------------------
+            const double* trow = tsm + size_t(t - g.t_first) * kNrBinsPad;
+#pragma unroll
+            for (int j = 0; j < 18; ++j) {
+                const int k = lane - 16 + 32 * j;
+                if (k <= 528) mrow[mrow_idx(k)] = (k >= 0 && k < kNrBins) ? trow[k] : 0.0;
             }
-            const double ex = a.x + p.x, ey = a.y - p.y, dx = a.x - p.x, dy = a.y + p.y;
-            const double2 cs = sm.split[k];
-            const double zr = ex - (dx * cs.y + dy * cs.x);
-            const double zi = ey + (dx * cs.x - dy * cs.y);
-            v[q] = make_double2(zr, -zi);
-        });
-        __syncwarp();
-        warp_fft512(v, sm.xbuf[warp], sm.tw512, sm.tw32h, lane);
-        double2* frow = reinterpret_cast<double2*>(frames + size_t(t - g.t_first) * kNrFft);
-        static_for<16>([&](auto iq) {
-            constexpr int q = decltype(iq)::value;
-            const int j = lane + 32 * q;
-            const double s0 = v[q].x * (1.0 / 1024.0), s1 = -v[q].y * (1.0 / 1024.0);
-            frow[j] = make_double2(s0 * sm.hann[2 * j], s1 * sm.hann[2 * j + 1]);
-        });
-        __syncwarp();
+            __syncwarp();
+            // ---- 33-tap frequency smoothing, 16 consecutive bins per lane (+ bin 512 on lane 31) ----
+            // taps applied in ascending tap order a = 0..32 (input bin k + 16 - a), like the separate pass did
+            double acc[17];
+#pragma unroll
+            for (int j = 0; j < 17; ++j) acc[j] = 0.0;
+            double* seg = mrow + 17 * lane + 17;                // bin 16 lane + m at seg[m + floor(m / 16)]
+            static_for<49>([&](auto im) {
+                constexpr int mm = 32 - decltype(im)::value;    // 32 .. -16
+                constexpr int off = mm + (mm >= 0 ? mm / 16 : -1);
+                if constexpr (mm <= 31) {
+                    const double in = seg[off];
+                    static_for<16>([&](auto ij) {
+                        constexpr int jj = decltype(ij)::value;
+                        constexpr int a = jj + 16 - mm;
+                        if constexpr (a >= 0 && a < kNrFreqTaps) acc[jj] = fma(c_smooth_f[a], in, acc[jj]);
+                    });
+                    if constexpr (mm >= 0) {
+                        if (lane == 31) acc[16] = fma(c_smooth_f[32 - mm], in, acc[16]);
+                    }
+                } else {
+                    if (lane == 31) acc[16] = fma(c_smooth_f[0], seg[off], acc[16]);
+                }
+            });
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 16; ++j) seg[j] = acc[j] * prop + one_minus_prop;
+            if (lane == 31) seg[17] = acc[16] * prop + one_minus_prop;
+            __syncwarp();
+            static_for<16>([&](auto iq) {
+                constexpr int q = decltype(iq)::value;
+                const double mk_ = mrow[mrow_idx(lane + 32 * q)];
+                x[q].x *= mk_; x[q].y *= mk_;
+            });
+            nyq *= mrow[mrow_idx(512)];
+            // inverse real split: Z'[k] = (X[k] + conj X[512-k]) + i e^{+2 pi i k/1024} (X[k] - conj X[512-k]);
+            // the inverse FFT is taken as conj(FFT(conj Z')), overall scale 1/1024.
+            double2 v[16];
+            static_for<16>([&](auto iq) {
+                constexpr int q = decltype(iq)::value;
+                const int k = lane + 32 * q;
+                const double2 a = x[q];
+                double2 p;
+                p.x = __shfl_sync(0xffffffffu, x[15 - q].x, src_lane);
+                p.y = __shfl_sync(0xffffffffu, x[15 - q].y, src_lane);
+                if (lane == 0) {
+                    if constexpr (q == 0) p = make_double2(nyq, 0.0);
+                    else p = x[16 - q];
+                }
+                const double ex = a.x + p.x, ey = a.y - p.y, dx = a.x - p.x, dy = a.y + p.y;
+                const double2 cs = sm.tab.split[k];
+                const double zr = ex - (dx * cs.y + dy * cs.x);
+                const double zi = ey + (dx * cs.x - dy * cs.y);
+                v[q] = make_double2(zr, -zi);
+            });
+            __syncwarp();
+            warp_fft512_rolled(v, xb, sm.tab.tw512, sm.tab.tw32h, lane);
+            // windowed frame -> this warp's tile (sample 2 j, 2 j + 1 at double2 index j)
+            static_for<16>([&](auto iq) {
+                constexpr int q = decltype(iq)::value;
+                constexpr int rq = bitrev(q, 4);
+                const int j = lane + 32 * q;
+                const double s0 = v[rq].x * (1.0 / 1024.0), s1 = -v[rq].y * (1.0 / 1024.0);
+                xb[j] = make_double2(s0 * sm.tab.hann[2 * j], s1 * sm.tab.hann[2 * j + 1]);
+            });
+        } else {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) xb[lane + 32 * q] = make_double2(0.0, 0.0);
+        }
+        __syncthreads();
+        // ---- overlap-add: block T0 - 2 + m gets segments 3,2,1,0 of local frames m-3 .. m (ascending frame order) ----
+        {
+            const int j = tid & (kNrHop - 1);
+            const double* carry_in = &sm.carry[cbuf][0][0];
+            double* carry_out = &sm.carry[cbuf ^ 1][0][0];
+            for (int m = tid / kNrHop; m < W + 3; m += kGroups) {
+                double acc = (m < 3) ? carry_in[m * kNrHop + j] : 0.0;
+#pragma unroll
+                for (int d = 3; d >= 0; --d) {
+                    const int f = m - d;
+                    if (f >= 0 && f < W) acc += reinterpret_cast<const double*>(sm.xbuf[f])[d * kNrHop + j];
+                }
+                if (m >= W) { carry_out[(m - W) * kNrHop + j] = acc; continue; }
+                const int h = T0 - 2 + m;
+                if (h < hb || h >= he) continue;
+                const int s_local = h * kNrHop + j - kNrPad;
+                if (s_local >= 0 && s_local < g.out_len) {
+                    const float y = float(acc / sm.wss[j]);
+                    out[s_local] = y;
+                    if (isfinite(y)) peak = fmaxf(peak, fabsf(y)); else bad = true;
+                }
+            }
+            cbuf ^= 1;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) peak = fmaxf(peak, __shfl_xor_sync(0xffffffffu, peak, o));
+    if (lane == 0) sm.red[warp] = peak;
+    if (bad) sm.bad = 1;
+    __syncthreads();
+    if (tid == 0) {
+        float mx = sm.red[0];
+        for (int w2 = 1; w2 < W; ++w2) mx = fmaxf(mx, sm.red[w2]);
+        atomicMax(reinterpret_cast<unsigned*>(&clean_peak[g.clip]), __float_as_uint(mx));
+        if (sm.bad) atomicOr(&clean_flag[g.clip], 1);
     }
 }
 
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-k_nr_overlap_add(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrScratch sc, float* __restrict__ clean,
-                 float* __restrict__ clean_peak, int32_t* __restrict__ clean_flag) {
-    __shared__ float s_max[8];
-    __shared__ int s_bad;
-    const int li = blockIdx.x;
-    const NrGeom g = nr_geom(cv, item0 + li, cpc);
-    const int s_local = blockIdx.y * 256 + threadIdx.x;
-    if (blockIdx.y * 256 >= g.out_len) return;
-    if (threadIdx.x == 0) s_bad = 0;
-    __syncthreads();
-    float mine = 0.f;
-    if (s_local < g.out_len) {
-        const int p = s_local + kNrPad;                       // padded-chunk coordinate
-        const int t_hi = (p + 512) / kNrHop;
-        const double* frames = sc.frames + size_t(li) * sc.ta_max * kNrFft;
-        double acc = 0.0;
-#pragma unroll
-        for (int d = 3; d >= 0; --d) {                        // ascending frame index, like librosa's __overlap_add
-            const int t = t_hi - d;
-            if (t >= g.t_first && t <= g.t_last) acc += frames[size_t(t - g.t_first) * kNrFft + (p - t * kNrHop + 512)];
-        }
-        const float y = float(acc / tb.wss[p & (kNrHop - 1)]);
-        clean[size_t(g.clip) * cv.clean_pitch + g.c0 + s_local] = y;
-        mine = fabsf(y);
-        if (!isfinite(y)) { s_bad = 1; mine = 0.f; }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mine = fmaxf(mine, __shfl_xor_sync(0xffffffffu, mine, o));
-    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mine;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float mx = s_max[0];
-        for (int w = 1; w < 8; ++w) mx = fmaxf(mx, s_max[w]);
-        atomicMax(reinterpret_cast<unsigned*>(&clean_peak[g.clip]), __float_as_uint(mx));
-        if (s_bad) atomicOr(&clean_flag[g.clip], 1);
-    }
-}
+constexpr int kApplyWarps = 16;
 
 __global__ void k_clean_init(float* clean_peak, int32_t* clean_flag, const ClipView cv) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -395,17 +473,12 @@ int nr_ta_max(int max_len) {
 
 size_t nr_scratch_bytes(int n_items, int ta_max) {
     auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
-    const size_t f = size_t(n_items) * ta_max;
-    return 2 * al(f * kNrBinsPad * 8) + al(f * kNrFft * 8);
+    return al(size_t(n_items) * ta_max * kNrBinsPad * 8);
 }
 
 void nr_scratch_carve(void* base, int n_items, int ta_max, NrScratch* out) {
-    auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
-    unsigned char* p = static_cast<unsigned char*>(base);
-    const size_t f = size_t(n_items) * ta_max;
-    out->mag = reinterpret_cast<double*>(p); p += al(f * kNrBinsPad * 8);
-    out->fwd = reinterpret_cast<double*>(p); p += al(f * kNrBinsPad * 8);
-    out->frames = reinterpret_cast<double*>(p);
+    (void)n_items;
+    out->mag = reinterpret_cast<double*>(base);
     out->ta_max = ta_max;
 }
 
@@ -423,28 +496,33 @@ cudaError_t launch_denoise(const DeviceTables& tb, const ClipView& cv, float* cl
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(k_nr_stft_mag, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(NrSmem)));
+        cudaError_t e = cudaFuncSetAttribute(k_nr_stft_mag, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(MagSmem)));
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_nr_apply_istft, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(NrSmem)));
+        e = cudaFuncSetAttribute(k_nr_apply_ola<kApplyWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 int(sizeof(ApplySmem<kApplyWarps>)));
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpyToSymbol(c_smooth_f, host_tables().smooth_f.data(), sizeof(double) * kNrFreqTaps);
         if (e != cudaSuccess) return e;
         attr_set[dev & 63] = true;
     }
+    if (sc.ta_max > kIirMaxCk << kIirCkShift) return cudaErrorInvalidValue;
     const int gy = (sc.ta_max + kFramesPerCta - 1) / kFramesPerCta;
     ClipView cvw = cv;
     cvw.clean = clean; cvw.clean_peak = clean_peak; cvw.clean_flag = clean_flag;
     { LaunchScope ls(kK_nr_stft_mag, stream);
-      k_nr_stft_mag<<<dim3(n_items, gy), kThreads, sizeof(NrSmem), stream>>>(tb, cvw, cpc, item0, sc); }
+      k_nr_stft_mag<<<dim3(n_items, gy), kThreads, sizeof(MagSmem), stream>>>(tb, cvw, cpc, item0, sc); }
     { LaunchScope ls(kK_nr_iir_mask, stream);
-      k_nr_iir_mask<<<dim3(n_items, (kNrBins + 127) / 128), 128, 0, stream>>>(tb, cvw, cpc, item0, sc, clean_flag); }
-    { LaunchScope ls(kK_nr_smooth, stream);
-      k_nr_smooth<<<dim3(n_items, (sc.ta_max + kSmoothRows - 1) / kSmoothRows), kThreads, 0, stream>>>(tb, cvw, cpc, item0, sc,
-                                                                                                      double(prop_decrease)); }
-    { LaunchScope ls(kK_nr_apply_istft, stream);
-      k_nr_apply_istft<<<dim3(n_items, gy), kThreads, sizeof(NrSmem), stream>>>(tb, cvw, cpc, item0, sc); }
+      k_nr_iir_mask<<<dim3(n_items, (kNrBins + kIirThreads - 1) / kIirThreads), kIirThreads, 0, stream>>>(tb, cvw, cpc, item0, sc,
+                                                                                                      clean_flag); }
+    // output blocks of 256 samples per chunk, split evenly over CTAs of about 16 W frames
     const int max_out = std::min(cv.max_len, kNrChunk);
-    { LaunchScope ls(kK_nr_overlap_add, stream);
-      k_nr_overlap_add<<<dim3(n_items, (max_out + 255) / 256), 256, 0, stream>>>(tb, cvw, cpc, item0, sc, clean, clean_peak,
-                                                                               clean_flag); }
+    const int n_blocks = (kNrPad + std::max(max_out, 1) - 1) / kNrHop - kNrPad / kNrHop + 1;
+    const int per_cta_target = 8 * kApplyWarps - 3;
+    const int n_cta = (n_blocks + per_cta_target - 1) / per_cta_target;
+    const int blocks_per_cta = (n_blocks + n_cta - 1) / n_cta;
+    { LaunchScope ls(kK_nr_apply_ola, stream);
+      k_nr_apply_ola<kApplyWarps><<<dim3(n_items, n_cta), kApplyWarps * 32, sizeof(ApplySmem<kApplyWarps>), stream>>>(
+          tb, cvw, cpc, item0, sc, double(prop_decrease), blocks_per_cta, clean, clean_peak, clean_flag); }
     return cudaGetLastError();
 }
 

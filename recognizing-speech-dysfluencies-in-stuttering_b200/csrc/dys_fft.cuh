@@ -192,6 +192,37 @@ __device__ __forceinline__ void warp_fft512(double2 (&v)[16], double2* xbuf, con
     static_for<16>([&](auto iq) { constexpr int q = decltype(iq)::value; v[q] = o[q]; });
 }
 
+// Compact-code variant of warp_fft512 (one copy of the 16-point butterfly code, 2-trip rolled
+// loop).  Result is left bit-reversed:  Z[lane + 32 q] = v[bitrev(q, 4)].
+__device__ __forceinline__ void warp_fft512_rolled(double2 (&v)[16], double2* xbuf, const double2* __restrict__ tw512,
+                                                   const double2* __restrict__ tw32h, int lane) {
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+        fft_reg<16, double>(v);
+        if (pass == 0) {
+            static_for<16>([&](auto ik) {
+                constexpr int kA = decltype(ik)::value;
+                constexpr int r = bitrev(kA, 4);
+                double2 val = v[r];
+                if constexpr (kA != 0) val = cmul(val, tw512[kA * 32 + lane]);
+                xbuf[kA * 33 + lane] = val;
+            });
+            __syncwarp();
+            const int kA = lane & 15, h = lane >> 4;
+            const double sgn = h ? -1.0 : 1.0;
+            static_for<16>([&](auto il) {
+                constexpr int l = decltype(il)::value;
+                const double2 a = xbuf[kA * 33 + l];
+                const double2 b = xbuf[kA * 33 + l + 16];
+                double2 d = mk<double>(a.x + sgn * b.x, a.y + sgn * b.y);
+                if constexpr (l != 0) d = cmul(d, tw32h[h * 16 + l]);
+                v[l] = d;
+            });
+            __syncwarp();
+        }
+    }
+}
+
 // Partner fetch for the real-FFT split: lane holding k = lane + 32 q needs Z[NH - k], which
 // lives in lane (32 - lane) & 31 at register Q-1-q (lane 0: its own register (Q - q) % Q).
 template <int Q>

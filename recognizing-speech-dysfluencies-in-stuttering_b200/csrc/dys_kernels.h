@@ -54,9 +54,7 @@ cudaError_t launch_features(const DeviceTables& tb, const ClipView& cv, int inst
 
 // Spectral-gate scratch for a sub-batch of chunks.
 struct NrScratch {
-    double* mag;       // [n_items][ta_max][kNrBinsPad]   |STFT| then raw sigmoid mask (in place)
-    double* fwd;       // [n_items][ta_max][kNrBinsPad]   forward IIR state, then the smoothed mask
-    double* frames;    // [n_items][ta_max][kNrFft]       windowed inverse frames
+    double* mag;       // [n_items][ta_max][kNrBinsPad]   |STFT|, then (in place) the time-smoothed sigmoid mask
     int ta_max;
 };
 size_t nr_scratch_bytes(int n_items, int ta_max);

@@ -10,7 +10,7 @@ namespace {
 
 const char* const kNames[kKernelCount] = {
     "k_feat_init", "k_frame_spectra", "k_tuning", "k_frame_cepstra", "k_clip_stats", "k_clean_init",
-    "k_nr_stft_mag", "k_nr_iir_mask", "k_nr_smooth", "k_nr_apply_istft", "k_nr_overlap_add", "k_quantize_pcm",
+    "k_nr_stft_mag", "k_nr_iir_mask", "k_nr_apply_ola", "k_quantize_pcm",
     "k_cmvn_partial", "k_cmvn_merge", "k_cmvn_finalize", "k_cmvn_apply"};
 
 struct Record {

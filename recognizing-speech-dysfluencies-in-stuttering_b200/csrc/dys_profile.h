@@ -18,9 +18,7 @@ enum KernelId : int {
     kK_clean_init,
     kK_nr_stft_mag,
     kK_nr_iir_mask,
-    kK_nr_smooth,
-    kK_nr_apply_istft,
-    kK_nr_overlap_add,
+    kK_nr_apply_ola,
     kK_quantize_pcm,
     kK_cmvn_partial,
     kK_cmvn_merge,
