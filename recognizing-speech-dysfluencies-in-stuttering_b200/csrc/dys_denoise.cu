@@ -182,13 +182,26 @@ k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
     // forward: f[t] = b A[t] + (1 - b) f[t-1],  f[-1] := A[0]  (lfilter_zi steady state; A[0] = 0 when padded)
     double prev = (g.t_first == 0) ? col[0] : 0.0;
     int i = 0;
-    for (; i + 8 <= Ta; i += 8) {
-        double a[8];
+    {   // batches of 8 rows, the next batch's loads in flight while the serial recurrence runs over the current one
+        double a[8], an[8];
+        if (Ta >= 8) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) a[u] = col[size_t(i + u) * P];
+            for (int u = 0; u < 8; ++u) a[u] = col[size_t(u) * P];
+        }
+        for (; i + 8 <= Ta; i += 8) {
+            const bool more = i + 16 <= Ta;
+            if (more) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) prev = b * a[u] + r * prev;
-        if (((i + 8) & ((1 << kIirCkShift) - 1)) == 0) ck[((i + 8) >> kIirCkShift) - 1][threadIdx.x] = prev;
+                for (int u = 0; u < 8; ++u) an[u] = col[size_t(i + 8 + u) * P];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) prev = b * a[u] + r * prev;
+            if (((i + 8) & ((1 << kIirCkShift) - 1)) == 0) ck[((i + 8) >> kIirCkShift) - 1][threadIdx.x] = prev;
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a[u] = an[u];
+            }
+        }
     }
     for (; i < Ta; ++i) {
         prev = b * col[size_t(i) * P] + r * prev;
@@ -219,33 +232,49 @@ k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
     // backward: S[t] = b f[t] + (1 - b) S[t+1]; the forward state is re-derived as f[t-1] = (f[t] - b A[t]) / (1 - b)
     // (error growth (1/r)^128 = 2.8 between check-points); row i+3 of the time-smoothed mask is complete once
     // the raw mask of row i is known, and overwrites |D| in place (row i+3 was consumed three steps earlier).
-    for (i = Ta - 1; i >= -3; --i) {
+    auto step = [&](int i_, double A, bool real_row) {
         double m0;
-        if (i >= 0) {
-            const double A = col[size_t(i) * P];
+        if (real_row) {
             const double S = b * fcur + r * nxt;
             nxt = S;
             const double above = (A - S) / S;
             m0 = 1.0 / (1.0 + exp(-(above + -2.0) * 10.0));
             bad |= isnan(m0);
-            if (i > 0) {
-                if ((i & ((1 << kIirCkShift) - 1)) == 0) fcur = ck[(i >> kIirCkShift) - 1][threadIdx.x];
+            if (i_ > 0) {
+                if ((i_ & ((1 << kIirCkShift) - 1)) == 0) fcur = ck[(i_ >> kIirCkShift) - 1][threadIdx.x];
                 else fcur = (fcur - b * A) * rinv;
             }
         } else {
-            m0 = virt(i);
+            m0 = virt(i_);
         }
 #pragma unroll
         for (int j = kNrTimeTaps - 1; j > 0; --j) w[j] = w[j - 1];
         w[0] = m0;
-        const int row = i + 3;
+        const int row = i_ + 3;
         if (row < Ta) {
             double acc = 0.0;
 #pragma unroll
             for (int bb = 0; bb < kNrTimeTaps; ++bb) acc += ft[bb] * w[kNrTimeTaps - 1 - bb];
             col[size_t(row) * P] = acc;
         }
+    };
+    {   // rows Ta-1 .. 0 in batches of 8 (loads of the next batch in flight during the current one); a batch's
+        // stores touch rows >= its lowest row + 3, all of them already in registers or consumed
+        double a[8], an[8];
+        int i0 = Ta - 1;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = (i0 - u >= 0) ? col[size_t(i0 - u) * P] : 0.0;
+        for (; i0 >= 0; i0 -= 8) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u) an[u] = (i0 - 8 - u >= 0) ? col[size_t(i0 - 8 - u) * P] : 0.0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (i0 - u >= 0) step(i0 - u, a[u], true);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] = an[u];
+        }
     }
+    for (int i_ = -1; i_ >= -3; --i_) step(i_, 0.0, false);
     if (bad) atomicOr(&clean_flag[g.clip], 1);
 }
 
@@ -302,11 +331,14 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
     for (int T0 = hb - 1; T0 - 2 < he; T0 += W) {
         const int t = T0 + warp;
         if (t >= g.t_first && t <= g.t_last && t <= he + 1) {
+            // the mask row is needed after the forward FFT: start pulling its 33 lines into L1 now
+            const double* trow = tsm + size_t(t - g.t_first) * kNrBinsPad;
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(trow + 16 * lane));
+            if (lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(trow + 512));
             double2 x[16];
             double nyq;
             nr_frame_stft(sm.tab, xb, base, vec_ok, g, t, lane, x, &nyq);
             // ---- time-smoothed mask row -> shared (zero halo: 'same' convolution) ------------------
-            const double* trow = tsm + size_t(t - g.t_first) * kNrBinsPad;
 #pragma unroll
             for (int j = 0; j < 18; ++j) {
                 const int k = lane - 16 + 32 * j;

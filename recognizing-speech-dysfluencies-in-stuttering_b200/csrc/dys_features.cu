@@ -127,53 +127,56 @@ k_frame_spectra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
     const int n = src.n;
 
     for (int t = t_begin + warp; t < t_end; t += kWarps) {
-        // ---- stage the windowed frame: xs[i] = (x[2i], x[2i+1]) * hann, zero centre padding -----
+        // ---- windowed frame straight into the FFT's register layout: v[m] = (x[2i], x[2i+1]) * hann, i = lane + 32 m.
+        // Interior frames issue all 32 coalesced 8-byte (PCM-16: 4-byte) loads before the first use; frames that
+        // overlap the zero centre padding or the clip end take the bounds-checked loop through shared memory.
         const int f0 = t * kHop - kNfft / 2;               // clip-relative index of the frame's first sample
         const bool interior = f0 >= 0 && f0 + kNfft <= n;
-        if (src.q16) {                                      // clean branch: int16 / 32768 (exact), as librosa.load reads the WAV
-            const int16_t* q = src.q16;
-#pragma unroll 4
-            for (int i = lane; i < kNfft / 2; i += 32) {
-                const int s = f0 + 2 * i;
-                float a = 0.f, b = 0.f;
-                if (interior) {
-                    const short2 p = __ldg(reinterpret_cast<const short2*>(q + s));
-                    a = float(p.x); b = float(p.y);
-                } else {
-                    if (s >= 0 && s < n) a = float(__ldg(q + s));
-                    if (s + 1 >= 0 && s + 1 < n) b = float(__ldg(q + s + 1));
-                }
-                const float2 w = hann2[i];
-                xbuf[i] = make_float2(a * (1.0f / 32768.0f) * w.x, b * (1.0f / 32768.0f) * w.y);
-            }
+        float2 v[32];
+        if (interior && src.q16) {                          // clean branch: int16 / 32768 (exact), as librosa.load reads the WAV
+            const short2* q2 = reinterpret_cast<const short2*>(src.q16 + f0);
+            short2 raw[32];
+            static_for<32>([&](auto im) { constexpr int m = decltype(im)::value; raw[m] = __ldg(q2 + lane + 32 * m); });
+            static_for<32>([&](auto im) {
+                constexpr int m = decltype(im)::value;
+                const float2 w = hann2[lane + 32 * m];
+                v[m] = make_float2(float(raw[m].x) * (1.0f / 32768.0f) * w.x, float(raw[m].y) * (1.0f / 32768.0f) * w.y);
+            });
+        } else if (interior && src.vec_ok) {
+            const float2* x2 = reinterpret_cast<const float2*>(src.f32 + f0);
+            static_for<32>([&](auto im) { constexpr int m = decltype(im)::value; v[m] = __ldg(x2 + lane + 32 * m); });
+            static_for<32>([&](auto im) {
+                constexpr int m = decltype(im)::value;
+                const float2 w = hann2[lane + 32 * m];
+                v[m] = make_float2(v[m].x * w.x, v[m].y * w.y);
+            });
         } else {
-            const float* x = src.f32;
-            const bool vec = interior && src.vec_ok;
-#pragma unroll 4
+#pragma unroll 2
             for (int i = lane; i < kNfft / 2; i += 32) {
                 const int s = f0 + 2 * i;
                 float a = 0.f, b = 0.f;
-                if (vec) {
-                    const float2 p = __ldg(reinterpret_cast<const float2*>(x + s));
-                    a = p.x; b = p.y;
+                if (src.q16) {
+                    if (s >= 0 && s < n) a = float(__ldg(src.q16 + s)) * (1.0f / 32768.0f);
+                    if (s + 1 >= 0 && s + 1 < n) b = float(__ldg(src.q16 + s + 1)) * (1.0f / 32768.0f);
                 } else {
-                    if (s >= 0 && s < n) a = __ldg(x + s);
-                    if (s + 1 >= 0 && s + 1 < n) b = __ldg(x + s + 1);
+                    if (s >= 0 && s < n) a = __ldg(src.f32 + s);
+                    if (s + 1 >= 0 && s + 1 < n) b = __ldg(src.f32 + s + 1);
                 }
-                nonfinite |= !(isfinite(a) && isfinite(b));
                 const float2 w = hann2[i];
                 xbuf[i] = make_float2(a * w.x, b * w.y);
             }
+            __syncwarp();
+            static_for<32>([&](auto im) {
+                constexpr int m = decltype(im)::value;
+                v[m] = xbuf[lane + 32 * m];
+            });
+            __syncwarp();
         }
-        __syncwarp();
-        float2 v[32];
-        static_for<32>([&](auto im) {
-            constexpr int m = decltype(im)::value;
-            v[m] = xbuf[lane + 32 * m];
-        });
-        __syncwarp();
 
         warp_fft1024_rolled(v, xbuf, sm.tw, lane);          // Z[lane + 32 q] = v[bitrev(q)]
+        // Z[0] = (sum of even samples, sum of odd samples) * window: non-finite iff some sample is
+        // (librosa.util.valid_audio raises on those -> zeros, pipeline1.py:237-239)
+        if (lane == 0) nonfinite |= !(isfinite(v[0].x) && isfinite(v[0].y));
 
         // ---- real split, two bins per pair: with E = (Z[k] + conj Z[1024-k]) / 2 and
         // T = e^{-2 pi i k / 2048} * (-i) (Z[k] - conj Z[1024-k]) / 2 :  X[k] = E + T,  X[1024-k] = conj(E - T).
@@ -354,10 +357,19 @@ k_tuning(const DeviceTables tb, FeatScratch sc) {
 }
 
 // ------------------------------------------------------------------------------------------
+constexpr int kCepFrames = 4;           // frames per warp iteration: every chroma weight load feeds 4 x 12 FMAs
+
 struct CepstraSmem {
     float dctT[kMels * kMfcc];          // [m][k]
-    float lrow[kWarps][kMels];
+    float4 lrow[kWarps][kCepFrames][kMels / 4];
 };
+
+__device__ __forceinline__ void chroma_fma(float (&acc)[kChroma], float p, const float4& w0, const float4& w1, const float4& w2) {
+    acc[0] = fmaf(w0.x, p, acc[0]); acc[1] = fmaf(w0.y, p, acc[1]); acc[2] = fmaf(w0.z, p, acc[2]);
+    acc[3] = fmaf(w0.w, p, acc[3]); acc[4] = fmaf(w1.x, p, acc[4]); acc[5] = fmaf(w1.y, p, acc[5]);
+    acc[6] = fmaf(w1.z, p, acc[6]); acc[7] = fmaf(w1.w, p, acc[7]); acc[8] = fmaf(w2.x, p, acc[8]);
+    acc[9] = fmaf(w2.y, p, acc[9]); acc[10] = fmaf(w2.z, p, acc[10]); acc[11] = fmaf(w2.w, p, acc[11]);
+}
 
 __global__ void __launch_bounds__(kThreads)
 k_frame_cepstra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch sc) {
@@ -380,55 +392,72 @@ k_frame_cepstra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
     const float* g_logmel = sc.logmel + size_t(li) * sc.t_max * kMels;
     float* g_mfcc = sc.mfcc + size_t(li) * sc.t_max * kMfcc;
     float* g_chroma = sc.chroma + size_t(li) * sc.t_max * kChroma;
-    float* lrow = sm.lrow[warp];
+    float4 (*lrow)[kMels / 4] = sm.lrow[warp];
 
-    for (int t = t_begin + warp; t < t_end; t += kWarps) {
-        // ---- clamp + DCT-II: lane k < 20 owns coefficient k --------------------------------------
+    for (int t0 = t_begin + warp * kCepFrames; t0 < t_end; t0 += kWarps * kCepFrames) {
+        const int nf = min(kCepFrames, t_end - t0);                      // warp-uniform
+        // ---- clamp + DCT-II: lane k < 20 owns coefficient k of the 4 frames ----------------------
 #pragma unroll
-        for (int g = 0; g < 4; ++g) lrow[lane + 32 * g] = fmaxf(g_logmel[size_t(t) * kMels + lane + 32 * g], thr);
+        for (int f = 0; f < kCepFrames; ++f) {
+            const int tt = min(t0 + f, t_end - 1);
+            const float4 L = reinterpret_cast<const float4*>(g_logmel + size_t(tt) * kMels)[lane];
+            lrow[f][lane] = make_float4(fmaxf(L.x, thr), fmaxf(L.y, thr), fmaxf(L.z, thr), fmaxf(L.w, thr));
+        }
         __syncwarp();
         if (lane < kMfcc) {
-            float acc = 0.f;
-#pragma unroll 8
-            for (int m = 0; m < kMels; ++m) acc = fmaf(lrow[m], sm.dctT[m * kMfcc + lane], acc);
-            g_mfcc[size_t(t) * kMfcc + lane] = acc;
-        }
-        // ---- chroma: 12 x 1025 projection, lane owns bins lane + 32 j ----------------------------
-        float acc[kChroma];
-#pragma unroll
-        for (int c = 0; c < kChroma; ++c) acc[c] = 0.f;
-        const float* gp = g_power + size_t(t) * kBinsPad;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 4
+            for (int m4 = 0; m4 < kMels / 4; ++m4) {
+                const float4 l0 = lrow[0][m4], l1 = lrow[1][m4], l2 = lrow[2][m4], l3 = lrow[3][m4];
+                const float d0 = sm.dctT[(4 * m4 + 0) * kMfcc + lane], d1 = sm.dctT[(4 * m4 + 1) * kMfcc + lane];
+                const float d2 = sm.dctT[(4 * m4 + 2) * kMfcc + lane], d3 = sm.dctT[(4 * m4 + 3) * kMfcc + lane];
+                a0 = fmaf(l0.x, d0, a0); a0 = fmaf(l0.y, d1, a0); a0 = fmaf(l0.z, d2, a0); a0 = fmaf(l0.w, d3, a0);
+                a1 = fmaf(l1.x, d0, a1); a1 = fmaf(l1.y, d1, a1); a1 = fmaf(l1.z, d2, a1); a1 = fmaf(l1.w, d3, a1);
+                a2 = fmaf(l2.x, d0, a2); a2 = fmaf(l2.y, d1, a2); a2 = fmaf(l2.z, d2, a2); a2 = fmaf(l2.w, d3, a2);
+                a3 = fmaf(l3.x, d0, a3); a3 = fmaf(l3.y, d1, a3); a3 = fmaf(l3.z, d2, a3); a3 = fmaf(l3.w, d3, a3);
+            }
+            g_mfcc[size_t(t0) * kMfcc + lane] = a0;
+            if (nf > 1) g_mfcc[size_t(t0 + 1) * kMfcc + lane] = a1;
+            if (nf > 2) g_mfcc[size_t(t0 + 2) * kMfcc + lane] = a2;
+            if (nf > 3) g_mfcc[size_t(t0 + 3) * kMfcc + lane] = a3;
+        }
+        // ---- chroma: 12 x 1025 projection of 4 frames, lane owns bins lane + 32 j -----------------
+        float acc[kCepFrames][kChroma];
+#pragma unroll
+        for (int f = 0; f < kCepFrames; ++f)
+#pragma unroll
+            for (int c = 0; c < kChroma; ++c) acc[f][c] = 0.f;
+        const float* gp[kCepFrames];
+#pragma unroll
+        for (int f = 0; f < kCepFrames; ++f) gp[f] = g_power + size_t(min(t0 + f, t_end - 1)) * kBinsPad;
+#pragma unroll 2
         for (int j = 0; j < 32; ++j) {
             const int k = lane + 32 * j;
-            const float p = gp[k];
             const float4 w0 = __ldg(&wtab[k * 3 + 0]), w1 = __ldg(&wtab[k * 3 + 1]), w2 = __ldg(&wtab[k * 3 + 2]);
-            acc[0] = fmaf(w0.x, p, acc[0]); acc[1] = fmaf(w0.y, p, acc[1]); acc[2] = fmaf(w0.z, p, acc[2]);
-            acc[3] = fmaf(w0.w, p, acc[3]); acc[4] = fmaf(w1.x, p, acc[4]); acc[5] = fmaf(w1.y, p, acc[5]);
-            acc[6] = fmaf(w1.z, p, acc[6]); acc[7] = fmaf(w1.w, p, acc[7]); acc[8] = fmaf(w2.x, p, acc[8]);
-            acc[9] = fmaf(w2.y, p, acc[9]); acc[10] = fmaf(w2.z, p, acc[10]); acc[11] = fmaf(w2.w, p, acc[11]);
+#pragma unroll
+            for (int f = 0; f < kCepFrames; ++f) chroma_fma(acc[f], gp[f][k], w0, w1, w2);
         }
         if (lane == 0) {
             const int k = 1024;
-            const float p = gp[k];
             const float4 w0 = __ldg(&wtab[k * 3 + 0]), w1 = __ldg(&wtab[k * 3 + 1]), w2 = __ldg(&wtab[k * 3 + 2]);
-            acc[0] = fmaf(w0.x, p, acc[0]); acc[1] = fmaf(w0.y, p, acc[1]); acc[2] = fmaf(w0.z, p, acc[2]);
-            acc[3] = fmaf(w0.w, p, acc[3]); acc[4] = fmaf(w1.x, p, acc[4]); acc[5] = fmaf(w1.y, p, acc[5]);
-            acc[6] = fmaf(w1.z, p, acc[6]); acc[7] = fmaf(w1.w, p, acc[7]); acc[8] = fmaf(w2.x, p, acc[8]);
-            acc[9] = fmaf(w2.y, p, acc[9]); acc[10] = fmaf(w2.z, p, acc[10]); acc[11] = fmaf(w2.w, p, acc[11]);
+#pragma unroll
+            for (int f = 0; f < kCepFrames; ++f) chroma_fma(acc[f], gp[f][k], w0, w1, w2);
         }
-        float cmax = 0.f;
 #pragma unroll
-        for (int c = 0; c < kChroma; ++c) {
+        for (int f = 0; f < kCepFrames; ++f) {
+            float cmax = 0.f;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-            cmax = fmaxf(cmax, fabsf(acc[c]));
+            for (int c = 0; c < kChroma; ++c) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc[f][c] += __shfl_xor_sync(0xffffffffu, acc[f][c], o);
+                cmax = fmaxf(cmax, fabsf(acc[f][c]));
+            }
+            if (cmax < FLT_MIN) cmax = 1.0f;                             // util.normalize: below tiny -> unscaled
+            float mine = 0.f;
+#pragma unroll
+            for (int c = 0; c < kChroma; ++c) if (lane == c) mine = acc[f][c];
+            if (lane < kChroma && f < nf) g_chroma[size_t(t0 + f) * kChroma + lane] = __fdiv_rn(mine, cmax);
         }
-        if (cmax < FLT_MIN) cmax = 1.0f;                                 // util.normalize: below tiny -> unscaled
-        float mine = 0.f;
-#pragma unroll
-        for (int c = 0; c < kChroma; ++c) if (lane == c) mine = acc[c];
-        if (lane < kChroma) g_chroma[size_t(t) * kChroma + lane] = __fdiv_rn(mine, cmax);
         __syncwarp();
     }
 }
