@@ -294,7 +294,7 @@ struct ApplySmem {
 };
 
 template <int W>
-__global__ void __launch_bounds__(W * 32, 1)
+__global__ void __launch_bounds__(W * 32, W == 8 ? 2 : 1)
 k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrScratch sc, double prop, int blocks_per_cta,
                float* __restrict__ clean, float* __restrict__ clean_peak, int32_t* __restrict__ clean_flag) {
     constexpr int kT = W * 32;
@@ -453,7 +453,7 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
     }
 }
 
-constexpr int kApplyWarps = 16;
+constexpr int kApplyWarps = 8;
 
 __global__ void k_clean_init(float* clean_peak, int32_t* clean_flag, const ClipView cv) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
