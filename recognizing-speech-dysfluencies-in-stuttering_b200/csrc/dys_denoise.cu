@@ -237,8 +237,8 @@ k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
         if (real_row) {
             const double S = b * fcur + r * nxt;
             nxt = S;
-            const double above = (A - S) / S;
-            m0 = 1.0 / (1.0 + exp(-(above + -2.0) * 10.0));
+            const double above = (A - S) * __drcp_rn(S);        // (A - S) / S to within one ulp; 0/0 and x/0 behave alike
+            m0 = __drcp_rn(1.0 + exp(-(above + -2.0) * 10.0));
             bad |= isnan(m0);
             if (i_ > 0) {
                 if ((i_ & ((1 << kIirCkShift) - 1)) == 0) fcur = ck[(i_ >> kIirCkShift) - 1][threadIdx.x];
@@ -283,14 +283,19 @@ k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
 // pad slot per 16 bins, so that lanes reading 16-bin segments at stride 17 doubles do not collide.
 __device__ __forceinline__ int mrow_idx(int k) { return k + (k >> 4) + 17; }
 
+// Per-warp tile: FFT exchange (8448 B), then mask row in (579 doubles) + smoothed mask out (545 doubles), then the
+// windowed output frame (8192 B).
+constexpr int kApplyTile = 576;                        // double2 units = 9216 B
+constexpr int kMaskOutOff = 580;                       // doubles
+
 template <int W>
 struct ApplySmem {
     NrTables tab;
     double wss[kNrHop];
-    double carry[2][3][kNrHop];
+    double carry[(W * 32) / kNrHop][3][kNrHop];        // double-buffered only when two thread groups share it
     float red[W];
     int bad;
-    double2 xbuf[W][kXbuf512];
+    double2 xbuf[W][kApplyTile];
 };
 
 template <int W>
@@ -346,39 +351,40 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
             }
             __syncwarp();
             // ---- 33-tap frequency smoothing, 16 consecutive bins per lane (+ bin 512 on lane 31) ----
-            // taps applied in ascending tap order a = 0..32 (input bin k + 16 - a), like the separate pass did
-            double acc[17];
-#pragma unroll
-            for (int j = 0; j < 17; ++j) acc[j] = 0.0;
+            // noisereduce's normalised triangle tri(16) is box17 (*) box17 / 289: two cascaded 17-bin running sums,
+            // b = B1(k + 8) leading and tr = B1(k - 9) trailing, 6 additions per output instead of 33 multiply-adds.
+            // (mask values lie in [0, 1]; the running sums stay within ~1e-15 of the direct sum.)
             double* seg = mrow + 17 * lane + 17;                // bin 16 lane + m at seg[m + floor(m / 16)]
-            static_for<49>([&](auto im) {
-                constexpr int mm = 32 - decltype(im)::value;    // 32 .. -16
-                constexpr int off = mm + (mm >= 0 ? mm / 16 : -1);
-                if constexpr (mm <= 31) {
-                    const double in = seg[off];
-                    static_for<16>([&](auto ij) {
-                        constexpr int jj = decltype(ij)::value;
-                        constexpr int a = jj + 16 - mm;
-                        if constexpr (a >= 0 && a < kNrFreqTaps) acc[jj] = fma(c_smooth_f[a], in, acc[jj]);
-                    });
-                    if constexpr (mm >= 0) {
-                        if (lane == 31) acc[16] = fma(c_smooth_f[32 - mm], in, acc[16]);
-                    }
-                } else {
-                    if (lane == 31) acc[16] = fma(c_smooth_f[0], seg[off], acc[16]);
-                }
-            });
-            __syncwarp();
+            auto in = [&](int m) { return seg[m + (m >= 0 ? m / 16 : -1)]; };
+            const double gain = prop * (1.0 / 289.0);
+            double* mout = mrow + kMaskOutOff + 17 * lane;      // smoothed bin k at mrow[kMaskOutOff + k + floor(k / 16)]
+            {
+                double b = in(-16);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) seg[j] = acc[j] * prop + one_minus_prop;
-            if (lane == 31) seg[17] = acc[16] * prop + one_minus_prop;
+                for (int m = -15; m <= 0; ++m) b += in(m);      // B1(-8)
+                double tr = b, o = b;
+#pragma unroll
+                for (int j = -7; j <= 8; ++j) { b = (b + in(j + 8)) - in(j - 9); o += b; }
+                mout[0] = o * gain + one_minus_prop;            // o = sum of B1(-8 .. 8)
+#pragma unroll
+                for (int k = 1; k <= 16; ++k) {
+                    b = (b + in(k + 16)) - in(k - 1);           // B1(k + 8)
+                    o = (o + b) - tr;
+                    if (k < 16) {
+                        mout[k] = o * gain + one_minus_prop;
+                        tr = (tr + in(k)) - in(k - 17);         // B1(k - 8)
+                    } else if (lane == 31) {
+                        mout[17] = o * gain + one_minus_prop;   // bin 512
+                    }
+                }
+            }
             __syncwarp();
             static_for<16>([&](auto iq) {
                 constexpr int q = decltype(iq)::value;
-                const double mk_ = mrow[mrow_idx(lane + 32 * q)];
+                const double mk_ = mrow[kMaskOutOff - 17 + mrow_idx(lane + 32 * q)];
                 x[q].x *= mk_; x[q].y *= mk_;
             });
-            nyq *= mrow[mrow_idx(512)];
+            nyq *= mrow[kMaskOutOff - 17 + mrow_idx(512)];
             // inverse real split: Z'[k] = (X[k] + conj X[512-k]) + i e^{+2 pi i k/1024} (X[k] - conj X[512-k]);
             // the inverse FFT is taken as conj(FFT(conj Z')), overall scale 1/1024.
             double2 v[16];
@@ -418,7 +424,7 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
         {
             const int j = tid & (kNrHop - 1);
             const double* carry_in = &sm.carry[cbuf][0][0];
-            double* carry_out = &sm.carry[cbuf ^ 1][0][0];
+            double* carry_out = &sm.carry[kGroups > 1 ? cbuf ^ 1 : 0][0][0];   // one group: thread j reads before it writes
             for (int m = tid / kNrHop; m < W + 3; m += kGroups) {
                 double acc = (m < 3) ? carry_in[m * kNrHop + j] : 0.0;
 #pragma unroll
@@ -436,7 +442,7 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
                     if (isfinite(y)) peak = fmaxf(peak, fabsf(y)); else bad = true;
                 }
             }
-            cbuf ^= 1;
+            if (kGroups > 1) cbuf ^= 1;
         }
         __syncthreads();
     }
@@ -485,9 +491,24 @@ __global__ void k_quantize_pcm(const ClipView cv, int16_t* __restrict__ clean_q,
     if (pk < FLT_MIN) pk = 1.0f;           // librosa.util.normalize: below tiny -> left unscaled
     const float* src = cv.clean + size_t(c) * cv.clean_pitch;
     int16_t* dst = clean_q + size_t(c) * cv.clean_pitch;
-    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
-        float q = rintf(__fdiv_rn(src[i], pk) * 32768.0f);
-        const int16_t v = int16_t(fminf(fmaxf(q, -32768.0f), 32767.0f));
+    auto quant = [pk](float x) {
+        const float q = rintf(__fdiv_rn(x, pk) * 32768.0f);
+        return int16_t(fminf(fmaxf(q, -32768.0f), 32767.0f));
+    };
+    // rows of the workspace are 256-byte aligned: 4 samples per thread (16-byte load, 8-byte store)
+    const int n4 = n >> 2;
+    const bool user_vec = user && (reinterpret_cast<uintptr_t>(user) & 7u) == 0;
+    for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n4; i += gridDim.y * blockDim.x) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(src) + i);
+        short4 q;
+        q.x = quant(x.x); q.y = quant(x.y); q.z = quant(x.z); q.w = quant(x.w);
+        reinterpret_cast<short4*>(dst)[i] = q;
+        if (user_vec) reinterpret_cast<short4*>(user)[i] = q;
+        else if (user) { user[4 * i] = q.x; user[4 * i + 1] = q.y; user[4 * i + 2] = q.z; user[4 * i + 3] = q.w; }
+    }
+    if (blockIdx.y == 0 && threadIdx.x < (n & 3)) {
+        const int i = 4 * n4 + threadIdx.x;
+        const int16_t v = quant(src[i]);
         dst[i] = v;
         if (user) user[i] = v;
     }
@@ -561,7 +582,7 @@ cudaError_t launch_denoise(const DeviceTables& tb, const ClipView& cv, float* cl
 cudaError_t launch_quantize_pcm(const ClipView& cv, int16_t* clean_q, int16_t* pcm, const int64_t* pcm_starts,
                                 cudaStream_t stream) {
     if (cv.n_clips <= 0) return cudaSuccess;
-    const int gy = std::max(1, std::min(64, (cv.max_len + 255) / 256));
+    const int gy = std::max(1, std::min(16, (cv.max_len / 4 + 255) / 256));
     LaunchScope ls(kK_quantize_pcm, stream);
     k_quantize_pcm<<<dim3(cv.n_clips, gy), 256, 0, stream>>>(cv, clean_q, pcm, pcm_starts);
     return cudaGetLastError();
