@@ -109,22 +109,26 @@ __device__ __forceinline__ void nr_frame_stft(const NrTables& sm, double2* xbuf,
         v[m] = make_double2(double(a) * sm.hann[j2], double(b) * sm.hann[j2 + 1]);
     });
     warp_fft512_rolled(v, xbuf, sm.tw512, sm.tw32h, lane);  // Z[lane + 32 q] = v[bitrev(q, 4)]
-    const int src_lane = (32 - lane) & 31;
+    // real split through the (now free) exchange tile: every lane publishes its Z and fetches the partner
+    // Z[512 - k] of each of its bins, so X[k] replaces Z[k] in place (no second register array, no shuffles).
     static_for<16>([&](auto iq) {
         constexpr int q = decltype(iq)::value;
-        constexpr int rq = bitrev(q, 4), rp = bitrev(15 - q, 4), r0 = bitrev((16 - q) & 15, 4);
+        xbuf[lane + 32 * q] = v[bitrev(q, 4)];
+    });
+    if (lane == 0) xbuf[512] = v[0];                        // Z[512] := Z[0]
+    __syncwarp();
+    static_for<16>([&](auto iq) {
+        constexpr int q = decltype(iq)::value;
         const int k = lane + 32 * q;
-        const double2 z = v[rq];
-        double2 p;
-        p.x = __shfl_sync(0xffffffffu, v[rp].x, src_lane);
-        p.y = __shfl_sync(0xffffffffu, v[rp].y, src_lane);
-        if (lane == 0) p = v[r0];
+        const double2 z = v[bitrev(q, 4)];
+        const double2 p = xbuf[512 - k];
         const double ex = z.x + p.x, ey = z.y - p.y, dx = z.x - p.x, dy = z.y + p.y;
         const double2 cs = sm.split[k];
         x[q] = make_double2(0.5 * (ex + (cs.x * dy - cs.y * dx)), 0.5 * (ey - (cs.x * dx + cs.y * dy)));
     });
-    const double z0x = __shfl_sync(0xffffffffu, v[0].x, 0), z0y = __shfl_sync(0xffffffffu, v[0].y, 0);
-    *nyq = z0x - z0y;
+    const double2 z0 = xbuf[512];
+    *nyq = z0.x - z0.y;
+    __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -326,7 +330,6 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
     float* out = clean + size_t(g.clip) * cv.clean_pitch + g.c0;
     double2* xb = sm.xbuf[warp];
     double* mrow = reinterpret_cast<double*>(xb);
-    const int src_lane = (32 - lane) & 31;
     const double one_minus_prop = 1.0 - prop;
     float peak = 0.f;
     bool bad = false;
@@ -387,18 +390,19 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
             nyq *= mrow[kMaskOutOff - 17 + mrow_idx(512)];
             // inverse real split: Z'[k] = (X[k] + conj X[512-k]) + i e^{+2 pi i k/1024} (X[k] - conj X[512-k]);
             // the inverse FFT is taken as conj(FFT(conj Z')), overall scale 1/1024.
+            __syncwarp();
+            static_for<16>([&](auto iq) {
+                constexpr int q = decltype(iq)::value;
+                xb[lane + 32 * q] = x[q];
+            });
+            if (lane == 0) xb[512] = make_double2(nyq, 0.0);
+            __syncwarp();
             double2 v[16];
             static_for<16>([&](auto iq) {
                 constexpr int q = decltype(iq)::value;
                 const int k = lane + 32 * q;
                 const double2 a = x[q];
-                double2 p;
-                p.x = __shfl_sync(0xffffffffu, x[15 - q].x, src_lane);
-                p.y = __shfl_sync(0xffffffffu, x[15 - q].y, src_lane);
-                if (lane == 0) {
-                    if constexpr (q == 0) p = make_double2(nyq, 0.0);
-                    else p = x[16 - q];
-                }
+                const double2 p = xb[512 - k];                  // X[512 - k]  (k = 0: the Nyquist bin)
                 const double ex = a.x + p.x, ey = a.y - p.y, dx = a.x - p.x, dy = a.y + p.y;
                 const double2 cs = sm.tab.split[k];
                 const double zr = ex - (dx * cs.y + dy * cs.x);
