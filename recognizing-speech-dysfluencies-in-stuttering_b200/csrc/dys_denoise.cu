@@ -121,9 +121,9 @@ __device__ __forceinline__ void nr_frame_stft(const NrTables& sm, double2* xbuf,
         constexpr int q = decltype(iq)::value;
         const int k = lane + 32 * q;
         const double2 z = v[bitrev(q, 4)];
-        const double2 p = xbuf[512 - k];
+        const double2 p = lds_once(&xbuf[512 - k]);
         const double ex = z.x + p.x, ey = z.y - p.y, dx = z.x - p.x, dy = z.y + p.y;
-        const double2 cs = sm.split[k];
+        const double2 cs = lds_once(&sm.split[k]);
         x[q] = make_double2(0.5 * (ex + (cs.x * dy - cs.y * dx)), 0.5 * (ey - (cs.x * dx + cs.y * dy)));
     });
     const double2 z0 = xbuf[512];
@@ -402,9 +402,9 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
                 constexpr int q = decltype(iq)::value;
                 const int k = lane + 32 * q;
                 const double2 a = x[q];
-                const double2 p = xb[512 - k];                  // X[512 - k]  (k = 0: the Nyquist bin)
+                const double2 p = lds_once(&xb[512 - k]);       // X[512 - k]  (k = 0: the Nyquist bin)
                 const double ex = a.x + p.x, ey = a.y - p.y, dx = a.x - p.x, dy = a.y + p.y;
-                const double2 cs = sm.tab.split[k];
+                const double2 cs = lds_once(&sm.tab.split[k]);
                 const double zr = ex - (dx * cs.y + dy * cs.x);
                 const double zi = ey + (dx * cs.x - dy * cs.y);
                 v[q] = make_double2(zr, -zi);

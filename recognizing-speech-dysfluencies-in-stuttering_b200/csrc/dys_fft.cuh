@@ -31,6 +31,20 @@ template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
     C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
 }
 
+// Shared-memory loads the compiler may neither duplicate nor re-issue: under register pressure ptxas
+// re-materialises plain LDS (two copies of every partner / table load in the real-FFT split), which
+// costs wavefronts on the unit these kernels are bound by.
+__device__ __forceinline__ double2 lds_once(const double2* p) {
+    double2 r;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(unsigned(__cvta_generic_to_shared(p))));
+    return r;
+}
+__device__ __forceinline__ float2 lds_once(const float2* p) {
+    float2 r;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "r"(unsigned(__cvta_generic_to_shared(p))));
+    return r;
+}
+
 // ---- compile-time loops -------------------------------------------------------------------
 template <typename F, int... I>
 __device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) {

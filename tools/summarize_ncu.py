@@ -55,7 +55,13 @@ def launches(path):
         print(f"{k},{cnt[k]},{v:.3f},{v / cnt[k]:.4f},{v / s:.4f}")
 
 
+SCALE = {"ns": ("ms", 1e-6), "us": ("ms", 1e-3), "ms": ("ms", 1.0), "s": ("ms", 1e3), "second": ("ms", 1e3),
+         "byte": ("Mbyte", 1e-6), "Kbyte": ("Mbyte", 1e-3), "Mbyte": ("Mbyte", 1.0), "Gbyte": ("Mbyte", 1e3),
+         "Tbyte": ("Mbyte", 1e6)}
+
+
 def full(paths):
+    """One row per profiled launch; times normalised to ms and byte counts to Mbyte (ncu picks a unit per report)."""
     print("# ncu --set full --clock-control none; one row per profiled launch")
     first = True
     for p in paths:
@@ -63,11 +69,21 @@ def full(paths):
         rows = list(csv.reader(io.StringIO(txt)))
         idx = {n: j for j, n in enumerate(rows[0])}
         cols = [m for m in KEY_METRICS if m in idx]
+        units = {c: rows[1][idx[c]] for c in cols}
         if first:
-            print("kernel," + ",".join(f"{c} [{rows[1][idx[c]]}]" for c in cols))
+            print("kernel," + ",".join(f"{c} [{SCALE.get(units[c], (units[c], 1.0))[0]}]" for c in cols))
             first = False
         for r in rows[2:]:
-            print(kname(r[idx["Kernel Name"]]) + "," + ",".join(r[idx[c]].replace(",", "") for c in cols))
+            vals = []
+            for c in cols:
+                v = r[idx[c]].replace(",", "")
+                if units[c] in SCALE and c not in ("launch__shared_mem_per_block_dynamic",):
+                    try:
+                        v = f"{float(v) * SCALE[units[c]][1]:.6g}"
+                    except ValueError:
+                        pass
+                vals.append(v)
+            print(kname(r[idx["Kernel Name"]]) + "," + ",".join(vals))
 
 
 if __name__ == "__main__":
