@@ -236,49 +236,69 @@ k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
     // backward: S[t] = b f[t] + (1 - b) S[t+1]; the forward state is re-derived as f[t-1] = (f[t] - b A[t]) / (1 - b)
     // (error growth (1/r)^128 = 2.8 between check-points); row i+3 of the time-smoothed mask is complete once
     // the raw mask of row i is known, and overwrites |D| in place (row i+3 was consumed three steps earlier).
-    auto step = [&](int i_, double A, bool real_row) {
-        double m0;
-        if (real_row) {
-            const double S = b * fcur + r * nxt;
-            nxt = S;
-            const double above = (A - S) * __drcp_rn(S);        // (A - S) / S to within one ulp; 0/0 and x/0 behave alike
-            m0 = __drcp_rn(1.0 + exp(-(above + -2.0) * 10.0));
-            bad |= isnan(m0);
-            if (i_ > 0) {
-                if ((i_ & ((1 << kIirCkShift) - 1)) == 0) fcur = ck[(i_ >> kIirCkShift) - 1][threadIdx.x];
-                else fcur = (fcur - b * A) * rinv;
-            }
-        } else {
-            m0 = virt(i_);
-        }
+    auto emit = [&](int row, double m0) {                // push the raw mask of row - 3, write the smoothed row
 #pragma unroll
         for (int j = kNrTimeTaps - 1; j > 0; --j) w[j] = w[j - 1];
         w[0] = m0;
-        const int row = i_ + 3;
-        if (row < Ta) {
-            double acc = 0.0;
+        double acc = 0.0;
 #pragma unroll
-            for (int bb = 0; bb < kNrTimeTaps; ++bb) acc += ft[bb] * w[kNrTimeTaps - 1 - bb];
-            col[size_t(row) * P] = acc;
+        for (int bb = 0; bb < kNrTimeTaps; ++bb) acc += ft[bb] * w[kNrTimeTaps - 1 - bb];
+        if (row < Ta) col[size_t(row) * P] = acc;
+    };
+    auto gate = [&](double A) {                           // one backward step at the current row: raw sigmoid mask
+        const double S = b * fcur + r * nxt;
+        nxt = S;
+        const double above = (A - S) * __drcp_rn(S);     // (A - S) / S to within one ulp; 0/0 and x/0 behave alike
+        const double m0 = __drcp_rn(1.0 + exp(-(above + -2.0) * 10.0));
+        bad |= isnan(m0);
+        return m0;
+    };
+    auto rewind = [&](int i_, double A) {                 // f[i_ - 1] from f[i_]
+        if (i_ > 0) {
+            if ((i_ & ((1 << kIirCkShift) - 1)) == 0) fcur = ck[(i_ >> kIirCkShift) - 1][threadIdx.x];
+            else fcur = (fcur - b * A) * rinv;
         }
     };
-    {   // rows Ta-1 .. 0 in batches of 8 (loads of the next batch in flight during the current one); a batch's
-        // stores touch rows >= its lowest row + 3, all of them already in registers or consumed
-        double a[8], an[8];
-        int i0 = Ta - 1;
-#pragma unroll
-        for (int u = 0; u < 8; ++u) a[u] = (i0 - u >= 0) ? col[size_t(i0 - u) * P] : 0.0;
-        for (; i0 >= 0; i0 -= 8) {
-#pragma unroll
-            for (int u = 0; u < 8; ++u) an[u] = (i0 - 8 - u >= 0) ? col[size_t(i0 - 8 - u) * P] : 0.0;
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (i0 - u >= 0) step(i0 - u, a[u], true);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) a[u] = an[u];
+    // prologue: the top rows one at a time until the remaining count is a multiple of 8 and no store can
+    // fall outside the clip's rows; then straight-line batches of 8 (rows 8m+7 .. 8m): the next batch's loads
+    // are in flight, the only branch is the check-point reload at the batch's last row, and a batch's stores
+    // touch rows >= 8m + 3, all already in registers or consumed.
+    int i_ = Ta - 1;
+    {
+        int pro = Ta & 7;
+        if (pro < 3 && Ta >= pro + 8) pro += 8;
+        if (Ta < 8) pro = Ta;
+        for (int c = 0; c < pro; ++c, --i_) {
+            const double A = col[size_t(i_) * P];
+            const double m0 = gate(A);
+            rewind(i_, A);
+            emit(i_ + 3, m0);
         }
     }
-    for (int i_ = -1; i_ >= -3; --i_) step(i_, 0.0, false);
+    if (i_ >= 7) {
+        double a[8], an[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = col[size_t(i_ - u) * P];
+        for (; i_ >= 7; i_ -= 8) {
+            const bool more = i_ >= 15;
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) an[u] = col[size_t(i_ - 8 - u) * P];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const double m0 = gate(a[u]);
+                if (u < 7) fcur = (fcur - b * a[u]) * rinv;      // rows 8m+7 .. 8m+1 are never check-point rows
+                else rewind(i_ - 7, a[7]);
+                emit(i_ - u + 3, m0);
+            }
+            if (more) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a[u] = an[u];
+            }
+        }
+    }
+    for (int v_ = -1; v_ >= -3; --v_) emit(v_ + 3, virt(v_));
     if (bad) atomicOr(&clean_flag[g.clip], 1);
 }
 
