@@ -3,7 +3,7 @@
 Follows /root/reference/pipeline1.py:470-473 (``StandardScaler().fit(X)`` then
 ``.transform(X)``; main1.py:848-852 likewise): per-feature float64 mean and
 population variance (ddof 0) over all clips, ``scale = sqrt(var)`` with zero
-variance -> 1.0, output ``(x - mean) / scale`` in float64.
+variance -> 1.0, output ``(x - mean) / scale`` in the input's dtype (float32 for the cache matrix).
 Pinned against output_results/scaler_after.pkl (tests/test_oracle_golden.py).
 """
 from __future__ import annotations
@@ -27,7 +27,16 @@ def fit(X: np.ndarray):
 
 
 def transform(X: np.ndarray, mean: np.ndarray, scale: np.ndarray) -> np.ndarray:
-    return (np.asarray(X, dtype=np.float64) - mean) / scale
+    """``StandardScaler.transform``: the output keeps X's dtype and the arithmetic runs in it
+    (``X -= mean_.astype(X.dtype); X /= scale_.astype(X.dtype)``, sklearn >= 1.4 as installed here;
+    checked bit-for-bit against sklearn in tests/test_oracle_golden.py).  The reference always passes
+    the float32 matrix np.vstack'ed from cache_features/ (pipeline1.py:455-473)."""
+    X = np.array(X, copy=True)
+    if X.dtype not in (np.float32, np.float64):
+        X = X.astype(np.float64)
+    X -= np.asarray(mean).astype(X.dtype)
+    X /= np.asarray(scale).astype(X.dtype)
+    return X
 
 
 def moments(X: np.ndarray) -> np.ndarray:

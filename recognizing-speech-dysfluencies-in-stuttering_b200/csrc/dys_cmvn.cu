@@ -71,7 +71,8 @@ __global__ void k_cmvn_apply(const float* __restrict__ feats, int64_t n_rows, co
     const int64_t i = int64_t(blockIdx.x) * blockDim.x + threadIdx.x;
     if (i >= n_rows * kFeat) return;
     const int f = int(i % kFeat);
-    out[i] = float((double(feats[i]) - mean[f]) / scale[f]);
+    // StandardScaler.transform on a float32 matrix: X -= mean_.astype(float32); X /= scale_.astype(float32)
+    out[i] = __fdiv_rn(__fsub_rn(feats[i], float(mean[f])), float(scale[f]));
 }
 
 }  // namespace

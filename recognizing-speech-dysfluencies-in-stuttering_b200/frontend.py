@@ -11,7 +11,7 @@ Same names, argument meaning and error behaviour as the reference's functions on
     cached_extract_features    pipeline1.py:429-440   (a closure there; module-level here)
 
 plus the batched entry points the reference lacks (``extract_features_batch``,
-``extract_features_host``, ``build_feature_cache``).  PyTorch is only plumbing here: device
+``extract_features_host``, ``extract_features_longform``, ``build_feature_cache``).  PyTorch is only plumbing here: device
 memory, streams, pinned host buffers.  All arithmetic runs in the CUDA library through its C
 ABI; there is no CPU fallback -- without the built library or a CUDA device calls raise.
 """
@@ -245,6 +245,43 @@ def extract_features_host(audio: torch.Tensor, denoise: bool = True, prop_decrea
             cur.wait_stream(s)
         cur.synchronize()
     return (out_raw, out_clean) if denoise else out_raw
+
+
+def extract_features_longform(recording, win: int = 48000, hop: int = 24000, denoise: bool = True,
+                              prop_decrease: float | None = None, rank: int = 0, world: int = 1, device=None):
+    """Long-form recordings (BASELINE config 4): sliding windows of ``win`` samples every ``hop`` samples, each an
+    independent clip for the reference's feature function (own centre padding, own top-dB maximum, own tuning,
+    own 30 000-sample denoise padding) -- the reference has no segmenter, this is the batched form of calling
+    ``extract_features`` / ``clean_audio_and_cache`` once per window.
+
+    The windows are addressed in place (starts + lengths into one sample buffer), so every sample of the recording
+    crosses PCIe and is stored in HBM once although windows overlap.  With ``world`` > 1 rank ``rank`` takes the
+    contiguous window range ``sharding.shard_range`` gives it and uploads only the samples that range covers.
+
+    Returns (starts int64 numpy [n_local], raw[n_local,149], clean[n_local,149] | None) -- CUDA float32 tensors."""
+    from . import sharding
+    if isinstance(recording, torch.Tensor):
+        rec = recording.reshape(-1)
+        if rec.dtype != torch.float32:
+            rec = rec.float()
+    else:
+        rec = torch.from_numpy(np.ascontiguousarray(recording, dtype=np.float32).reshape(-1))
+    all_starts = np.asarray(sharding.sliding_windows(int(rec.numel()), win, hop), dtype=np.int64)
+    lo, hi = sharding.shard_range(len(all_starts), rank, world)
+    starts = all_starts[lo:hi]
+    dev = _device(device if device is not None else (rec.device if rec.is_cuda else None))
+    if len(starts) == 0:
+        empty = torch.zeros((0, FEATURE_LEN), dtype=torch.float32, device=dev)
+        return starts, empty, (empty.clone() if denoise else None)
+    s0, s1 = int(starts[0]), int(starts[-1]) + win
+    with torch.cuda.device(dev):
+        span = rec[s0:s1].to(dev, non_blocking=True)
+        lens = np.full(len(starts), win, dtype=np.int32)
+        out = extract_features_batch(span, lengths=lens, starts=starts - s0, denoise=denoise, prop_decrease=prop_decrease,
+                                     device=dev)
+    if denoise:
+        return starts, out[0], out[1]
+    return starts, out, None
 
 
 _streams: dict = {}

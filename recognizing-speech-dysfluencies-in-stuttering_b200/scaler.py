@@ -113,3 +113,45 @@ class GlobalScaler:
 
     def fit_transform(self, X: torch.Tensor) -> torch.Tensor:
         return self.fit(X).transform(X)
+
+    def to_sklearn(self):
+        """A fitted ``sklearn.preprocessing.StandardScaler`` carrying this fit, i.e. the object the reference
+        pickles as ``output_results/scaler_after.pkl`` (main1.py:851) and its sidebar predictor reloads
+        (main1.py:958-987): the reference scripts keep working on statistics computed on the GPUs."""
+        if self.mean_ is None:
+            raise RuntimeError("GlobalScaler.to_sklearn called before fit")
+        from sklearn.preprocessing import StandardScaler
+        sk = StandardScaler()
+        sk.mean_ = self.mean_.cpu().numpy().copy()
+        sk.var_ = self.var_.cpu().numpy().copy()
+        sk.scale_ = self.scale_.cpu().numpy().copy()
+        sk.n_samples_seen_ = np.int64(self.n_samples_seen_)
+        sk.n_features_in_ = FEATURE_LEN
+        return sk
+
+
+def classifier_inputs(X: torch.Tensor, scaler: "GlobalScaler | None" = None, group=None, gather: bool = True):
+    """The reference classifier's input loader (pipeline1.py:455-473; main1.py:847-852,987) for features that
+    are already on the GPUs: fit the global scaler over every rank's rows (one all-reduce), standardise on the
+    device, and hand sklearn a host float32 matrix in the reference's row order.
+
+    X      this rank's float32 [N_rank, 149] CUDA tensor (rows in shard order, see sharding.shard_range)
+    scaler a fitted GlobalScaler to apply (inference: main1.py:987) or None to fit one here (training)
+    gather True: every rank receives all ranks' standardised rows (all-gather of the row blocks)
+    Returns (Z float32 numpy [N or N_rank, 149], scaler)."""
+    import torch.distributed as dist
+    if scaler is None:
+        scaler = GlobalScaler(group).fit(X)
+    Z = scaler.transform(X)
+    if gather and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        world = dist.get_world_size(group)
+        counts = torch.zeros(world, dtype=torch.int64, device=Z.device)
+        counts[dist.get_rank(group)] = Z.shape[0]
+        dist.all_reduce(counts, group=group)
+        blocks = [torch.empty((int(c), FEATURE_LEN), dtype=Z.dtype, device=Z.device) for c in counts.tolist()]
+        dist.all_gather(blocks, Z, group=group)
+        Z = torch.cat(blocks, dim=0)
+    host = torch.empty(Z.shape, dtype=Z.dtype).pin_memory()
+    host.copy_(Z, non_blocking=True)
+    torch.cuda.current_stream(Z.device).synchronize()
+    return host.numpy(), scaler

@@ -13,6 +13,9 @@ Outputs (committed; /root/reference does not exist on the GPU box):
       ``StandardScaler().fit`` at pipeline1.py:471, rebuilt from cache_features/ in
       sorted-path order, duplicates included) with mean_/var_/scale_ unpickled from
       output_results/scaler_after.pkl.
+  tests/golden/ref_classifier_after.npz -- the class label of each of those 905 rows and the accuracy /
+      log-loss the reference published for the cleaned features (output_results/metrics_summary.csv):
+      the end-to-end golden of the classifier input loader.
 Only data is copied, never reference source code.
 """
 import glob
@@ -71,6 +74,18 @@ def main():
     np.savez_compressed(os.path.join(HERE, "ref_scaler_after.npz"), X=X, mean=sc.mean_, var=sc.var_,
                         scale=sc.scale_, n=np.int64(sc.n_samples_seen_))
     print("scaler rows:", X.shape, "n_samples_seen:", sc.n_samples_seen_)
+
+    # classifier golden: labels of those rows (directory names, pipeline1.py:362-366) and the metrics the
+    # reference published for the cleaned features (output_results/metrics_summary.csv, written at
+    # pipeline1.py:533-535 after RandomForest(200, random_state=42) etc. on the stratified 80/20 split)
+    import csv
+    labels = np.asarray([os.path.basename(os.path.dirname(p)) for p in files])
+    rows_m = list(csv.DictReader(open(f"{REF}/output_results/metrics_summary.csv")))
+    after = {r["model"]: (float(r["accuracy"]), float(r["test_loss"])) for r in rows_m if r["dataset"] == "after"}
+    np.savez_compressed(os.path.join(HERE, "ref_classifier_after.npz"), labels=labels,
+                        models=np.asarray(list(after)), accuracy=np.asarray([after[m][0] for m in after]),
+                        test_loss=np.asarray([after[m][1] for m in after]))
+    print("classifier golden:", {m: after[m] for m in after})
 
 
 if __name__ == "__main__":

@@ -160,8 +160,30 @@ def test_scaler_golden(fe, pkg, torch_cuda, golden_dir):
     np.testing.assert_allclose(sc.scale_.cpu().numpy(), g["scale"], rtol=1e-11, atol=1e-13)
     assert np.all(sc.scale_.cpu().numpy()[144:] == 1.0)
     Z = sc.transform(X).cpu().numpy()
-    ref = ocmvn.transform(g["X"], g["mean"], g["scale"]).astype(np.float32)
-    np.testing.assert_allclose(Z, ref, atol=2e-6, rtol=1e-6)
+    np.testing.assert_array_equal(Z, ocmvn.transform(g["X"], g["mean"], g["scale"]))      # sklearn's float32 arithmetic
+
+
+def test_classifier_feed_reproduces_published_metrics(pkg, torch_cuda, golden_dir):
+    """features on the GPU -> GlobalScaler (fit + apply on the device) -> host matrix -> the
+    reference's classifier (pipeline1.py:476-531).  On the reference's own cached features this must give the
+    accuracy / log-loss the reference published, and the exported sklearn scaler must equal its scaler_after.pkl."""
+    from test_oracle_golden import _published_rf_metrics
+    g = np.load(os.path.join(golden_dir, "ref_scaler_after.npz"))
+    c = np.load(os.path.join(golden_dir, "ref_classifier_after.npz"))
+    X = torch_cuda.from_numpy(g["X"]).cuda()
+    Z, sc = pkg.scaler.classifier_inputs(X)
+    assert Z.dtype == np.float32 and Z.shape == (905, 149)
+    np.testing.assert_array_equal(Z, ocmvn.transform(g["X"], *ocmvn.fit(g["X"])[0:3:2]))
+    acc, loss = _published_rf_metrics(Z, c["labels"])
+    i = list(c["models"]).index("RandomForest")
+    assert abs(acc - float(c["accuracy"][i])) < 1e-9 and abs(loss - float(c["test_loss"][i])) < 1e-12
+    sk = sc.to_sklearn()
+    assert sk.n_samples_seen_ == 905 and sk.n_features_in_ == 149
+    np.testing.assert_allclose(sk.mean_, g["mean"], rtol=1e-13, atol=1e-13)
+    np.testing.assert_allclose(sk.scale_, g["scale"], rtol=1e-11, atol=1e-13)
+    np.testing.assert_array_equal(sk.transform(g["X"][:7]), Z[:7])                       # inference path, main1.py:987
+    Z2, _ = pkg.scaler.classifier_inputs(X[:5], scaler=sc)
+    np.testing.assert_array_equal(Z2, Z[:5])
 
 
 # ---------------------------------------------------------------------------------------------
@@ -307,6 +329,30 @@ def test_sliding_windows_need_no_copy(fe, pkg, synth, torch_cuda):
     b_raw, b_clean = fe.extract_features_batch(copies, denoise=True)
     assert torch.equal(a_raw, b_raw) and torch.equal(a_clean, b_clean)
     _assert_feature_parity(a_raw[4].cpu().numpy(), ofeat.extract_features(copies[4]), "window 4")
+
+
+def test_longform_windows_shard_like_one_gpu(fe, pkg, synth, torch_cuda):
+    """BASELINE config 4 in small: a recording cut into 48 000 / 24 000 windows; two emulated ranks (contiguous
+    window ranges, each uploading only its own span) give bit-for-bit the single-rank rows, every window equals
+    the stand-alone clip, and the global scaler over all windows matches a float64 host StandardScaler."""
+    torch = torch_cuda
+    rec = np.concatenate([synth.synth_clip(300 + i) for i in range(7)])[:-1234]     # 20.9 s, not a multiple of hop
+    s_all, raw, clean = fe.extract_features_longform(rec)
+    assert list(s_all) == pkg.sharding.sliding_windows(len(rec)) and raw.shape == clean.shape == (len(s_all), 149)
+    parts = [fe.extract_features_longform(torch.from_numpy(rec).pin_memory(), rank=r, world=2) for r in range(2)]
+    assert np.array_equal(np.concatenate([p[0] for p in parts]), s_all)
+    assert torch.equal(torch.cat([p[1] for p in parts]), raw) and torch.equal(torch.cat([p[2] for p in parts]), clean)
+    k = len(s_all) // 2
+    one = rec[s_all[k]:s_all[k] + 48000]
+    _assert_feature_parity(raw[k].cpu().numpy(), ofeat.extract_features(one), "window raw")
+    _assert_feature_parity(clean[k].cpu().numpy(), ofeat.extract_features(oden.clean_then_load(one)), "window clean")
+    sc = pkg.scaler.GlobalScaler().fit(clean)
+    mean, var, scale, n = ocmvn.fit(clean.cpu().numpy())
+    assert sc.n_samples_seen_ == n == len(s_all)
+    np.testing.assert_allclose(sc.mean_.cpu().numpy(), mean, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(sc.scale_.cpu().numpy(), scale, rtol=1e-9, atol=1e-12)
+    s_none, r_none, c_none = fe.extract_features_longform(rec[:1000], denoise=False)
+    assert len(s_none) == 0 and r_none.shape == (0, 149) and c_none is None
 
 
 def test_host_streaming_path_equals_device_path(fe, synth, torch_cuda):

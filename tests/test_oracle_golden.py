@@ -56,6 +56,36 @@ def test_scaler_golden_bit_exact(golden_dir):
     np.testing.assert_allclose(s2, scale, rtol=1e-9, atol=1e-12)
 
 
+def _published_rf_metrics(Z, labels):
+    """The reference's 'after' RandomForest leg (pipeline1.py:462-531): LabelEncoder, stratified 80/20 split with
+    random_state=42, RandomForestClassifier(200, random_state=42) -> (accuracy %, log-loss)."""
+    from sklearn.ensemble import RandomForestClassifier
+    from sklearn.metrics import accuracy_score, log_loss
+    from sklearn.model_selection import train_test_split
+    from sklearn.preprocessing import LabelEncoder
+    y = LabelEncoder().fit_transform(labels)
+    Xtr, Xte, ytr, yte = train_test_split(Z, y, test_size=0.2, stratify=y, random_state=42)
+    rf = RandomForestClassifier(n_estimators=200, random_state=42).fit(Xtr, ytr)
+    return float(accuracy_score(yte, rf.predict(Xte)) * 100.0), float(log_loss(yte, rf.predict_proba(Xte)))
+
+
+def test_classifier_feed_reproduces_published_metrics(golden_dir):
+    """Scaler apply + the reference classifier on the reference's own cached features reproduces the accuracy and
+    log-loss the reference published (output_results/metrics_summary.csv): pins the classifier input loader."""
+    from sklearn.preprocessing import StandardScaler
+    g = np.load(os.path.join(golden_dir, "ref_scaler_after.npz"))
+    c = np.load(os.path.join(golden_dir, "ref_classifier_after.npz"))
+    mean, var, scale, _ = cmvn.fit(g["X"])
+    Z = cmvn.transform(g["X"], mean, scale)
+    assert Z.dtype == np.float32
+    assert np.array_equal(Z, StandardScaler().fit(g["X"]).transform(g["X"]))         # bit-for-bit sklearn
+    acc, loss = _published_rf_metrics(Z, c["labels"])
+    i = list(c["models"]).index("RandomForest")
+    assert abs(acc - float(c["accuracy"][i])) < 1e-9 and abs(loss - float(c["test_loss"][i])) < 1e-12
+    assert len(c["labels"]) == 905 and sorted(set(c["labels"])) == ["Prolongatio sample", "syllable repetition",
+                                                                    "word repetition"]
+
+
 def test_wav_round_trip_and_full_scale_property(tmp_path, golden_dir):
     g = np.load(os.path.join(golden_dir, "ref_clean_pairs.npz"))
     offs = g["offsets"]

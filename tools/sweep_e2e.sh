@@ -1,0 +1,9 @@
+for c in 500 1000 1250 2000 2500 5000; do
+  echo "== e2e-chunk $c"
+  python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-chunk $c 2>&1 | python -c "
+import sys,json
+for ln in sys.stdin:
+    if ln.startswith('{'):
+        d=json.loads(ln); print('dev ms',round(d['ms_per_step'],2),'e2e ms',round(d['e2e']['ms_per_step'],2),'raw_only ms',round(d['raw_only']['ms_per_step'],2))
+"
+done
