@@ -96,7 +96,8 @@ DYS_API int dys_cmvn_accumulate(const float* d_feats, int64_t n_rows, const doub
                         void* stream);
 /* mean_/scale_ from (all-reduced) moments; constant features get scale 1.0 like sklearn. */
 DYS_API int dys_cmvn_finalize(const double* d_acc, const double* d_shift, double* d_mean, double* d_scale, void* stream);
-/* StandardScaler.transform                                       [pipeline1.py:472-473] */
+/* StandardScaler.transform on the float32 feature matrix      [pipeline1.py:472-473, main1.py:987]
+ * (scikit-learn's arithmetic: mean_ and scale_ are cast to float32, then x - mean, then / scale, each rounded to float32) */
 DYS_API int dys_cmvn_apply(const float* d_feats, int64_t n_rows, const double* d_mean, const double* d_scale, float* d_out,
                    void* stream);
 
