@@ -152,16 +152,19 @@ k_nr_stft_mag(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
     const float* base = cv.audio + cv.starts[g.clip];
     const bool vec_ok = (reinterpret_cast<uintptr_t>(base) & 7u) == 0 && (g.c0 & 1) == 0;
     double* mag = sc.mag + size_t(li) * sc.ta_max * kNrBinsPad;
+    double2* spec = sc.spec + size_t(li) * sc.ta_max * kNrBinsPad;
     for (int t = t_begin + warp; t < t_end; t += kWarps) {
         double2 x[16];
         double nyq;
         nr_frame_stft(sm.tab, sm.xbuf[warp], base, vec_ok, g, t, lane, x, &nyq);
         double* row = mag + size_t(t - g.t_first) * kNrBinsPad;
+        double2* srow = spec + size_t(t - g.t_first) * kNrBinsPad;
         static_for<16>([&](auto iq) {
             constexpr int q = decltype(iq)::value;
+            srow[lane + 32 * q] = x[q];
             row[lane + 32 * q] = sqrt(x[q].x * x[q].x + x[q].y * x[q].y);
         });
-        if (lane == 0) row[512] = fabs(nyq);
+        if (lane == 0) { srow[512] = make_double2(nyq, 0.0); row[512] = fabs(nyq); }
         __syncwarp();
     }
 }
@@ -344,9 +347,8 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
     for (int i = tid; i < kNrHop; i += kT) sm.wss[i] = tb.wss[i];
     if (tid == 0) sm.bad = 0;
     __syncthreads();
-    const float* base = cv.audio + cv.starts[g.clip];
-    const bool vec_ok = (reinterpret_cast<uintptr_t>(base) & 7u) == 0 && (g.c0 & 1) == 0;
     const double* tsm = sc.mag + size_t(li) * sc.ta_max * kNrBinsPad;
+    const double2* spec = sc.spec + size_t(li) * sc.ta_max * kNrBinsPad;
     float* out = clean + size_t(g.clip) * cv.clean_pitch + g.c0;
     double2* xb = sm.xbuf[warp];
     double* mrow = reinterpret_cast<double*>(xb);
@@ -363,9 +365,14 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
             const double* trow = tsm + size_t(t - g.t_first) * kNrBinsPad;
             asm volatile("prefetch.global.L1 [%0];" ::"l"(trow + 16 * lane));
             if (lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(trow + 512));
+            // the frame's spectrum was stored by k_nr_stft_mag: its 16 + 1 loads are in flight while the mask row is smoothed
+            const double2* srow = spec + size_t(t - g.t_first) * kNrBinsPad;
             double2 x[16];
-            double nyq;
-            nr_frame_stft(sm.tab, xb, base, vec_ok, g, t, lane, x, &nyq);
+            static_for<16>([&](auto iq) {
+                constexpr int q = decltype(iq)::value;
+                x[q] = __ldg(srow + lane + 32 * q);
+            });
+            double nyq = __ldg(&srow[512].x);
             // ---- time-smoothed mask row -> shared (zero halo: 'same' convolution) ------------------
 #pragma unroll
             for (int j = 0; j < 18; ++j) {
@@ -550,12 +557,14 @@ int nr_ta_max(int max_len) {
 
 size_t nr_scratch_bytes(int n_items, int ta_max) {
     auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
-    return al(size_t(n_items) * ta_max * kNrBinsPad * 8);
+    return al(size_t(n_items) * ta_max * kNrBinsPad * 8) + al(size_t(n_items) * ta_max * kNrBinsPad * 16);
 }
 
 void nr_scratch_carve(void* base, int n_items, int ta_max, NrScratch* out) {
-    (void)n_items;
-    out->mag = reinterpret_cast<double*>(base);
+    auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
+    unsigned char* p = static_cast<unsigned char*>(base);
+    out->mag = reinterpret_cast<double*>(p); p += al(size_t(n_items) * ta_max * kNrBinsPad * 8);
+    out->spec = reinterpret_cast<double2*>(p);
     out->ta_max = ta_max;
 }
 

@@ -55,6 +55,7 @@ cudaError_t launch_features(const DeviceTables& tb, const ClipView& cv, int inst
 // Spectral-gate scratch for a sub-batch of chunks.
 struct NrScratch {
     double* mag;       // [n_items][ta_max][kNrBinsPad]   |STFT|, then (in place) the time-smoothed sigmoid mask
+    double2* spec;     // [n_items][ta_max][kNrBinsPad]   complex STFT (read back when the mask is applied)
     int ta_max;
 };
 size_t nr_scratch_bytes(int n_items, int ta_max);
