@@ -27,6 +27,23 @@ template <typename T> using cx = typename cx_of<T>::type;
 template <typename T> __device__ __forceinline__ cx<T> mk(T x, T y) { cx<T> r; r.x = x; r.y = y; return r; }
 template <typename C> __device__ __forceinline__ C cadd(C a, C b) { a.x += b.x; a.y += b.y; return a; }
 template <typename C> __device__ __forceinline__ C csub(C a, C b) { a.x -= b.x; a.y -= b.y; return a; }
+// Blackwell packed fp32: one FADD2 adds both halves of a complex number (sm_100a add.f32x2, IEEE round-to-nearest
+// per lane like two FADDs).  The FMA pipe time is the same, the issue slots are halved -- and the fp32 FFT kernel is
+// issue-bound.
+#ifndef DYS_NO_F32X2
+template <> __device__ __forceinline__ float2 cadd<float2>(float2 a, float2 b) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; add.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+template <> __device__ __forceinline__ float2 csub<float2>(float2 a, float2 b) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; sub.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
+#endif
 template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
     C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
 }
