@@ -277,6 +277,50 @@ def test_c_abi_direct_and_workspace_contract(pkg, fe, synth, torch_cuda):
     assert not raw[1].any() and not raw[2].any()
 
 
+def test_no_write_outside_declared_buffers(pkg, synth, torch_cuda):
+    """compute-sanitizer is closed on this pool, so overruns are caught with guard bands: every buffer handed to the
+    C ABI sits inside a larger allocation filled with a pattern, and the pattern must survive -- for ragged clips,
+    a clip longer than one gate chunk's frame budget and the minimal workspace (most sub-batches)."""
+    torch = torch_cuda
+    lib = pkg._lib.load()
+    GUARD = 1 << 16
+    lens = [48000, 4095, 50001, 16385, 1, 70000]
+    clips = [synth.synth_clip(900 + i, n) for i, n in enumerate(lens)]
+    n, L = len(clips), max(lens)
+    starts = np.concatenate(([0], np.cumsum([(x + 3) & ~3 for x in lens])[:-1])).astype(np.int64)
+    buf = np.zeros(int(starts[-1]) + lens[-1], np.float32)
+    for c, s0 in zip(clips, starts):
+        buf[s0:s0 + len(c)] = c
+    d_audio = torch.from_numpy(buf).cuda()
+    d_starts, d_lens = torch.from_numpy(starts).cuda(), torch.tensor(lens, dtype=torch.int32, device="cuda")
+    pcm_starts = np.concatenate(([0], np.cumsum(lens)[:-1])).astype(np.int64)
+    d_pcm_starts = torch.from_numpy(pcm_starts).cuda()
+
+    def guarded(nbytes):
+        t = torch.full((nbytes + 2 * GUARD,), 0xA5, dtype=torch.uint8, device="cuda")
+        return t, t[GUARD:GUARD + nbytes]
+
+    def intact(t, nbytes):
+        return bool((t[:GUARD] == 0xA5).all()) and bool((t[GUARD + nbytes:] == 0xA5).all())
+
+    for ws_bytes in (lib.dys_workspace_min_bytes(n, L, 1), lib.dys_workspace_bytes(n, L, 1)):
+        sizes = dict(ws=ws_bytes, raw=n * 149 * 4, clean=n * 149 * 4, st=2 * n * 4, pcm=sum(lens) * 2)
+        bufs = {k: guarded(v) for k, v in sizes.items()}
+        rc = lib.dys_features_raw_clean(d_audio.data_ptr(), d_starts.data_ptr(), d_lens.data_ptr(), n, L, ctypes.c_float(1.0),
+                                        bufs["raw"][1].data_ptr(), bufs["clean"][1].data_ptr(), bufs["st"][1].data_ptr(),
+                                        bufs["pcm"][1].data_ptr(), d_pcm_starts.data_ptr(), bufs["ws"][1].data_ptr(),
+                                        ws_bytes, None)
+        assert rc == 0, lib.dys_last_error()
+        torch.cuda.synchronize()
+        for k, v in sizes.items():
+            assert intact(bufs[k][0], v), f"{k} buffer overrun (workspace {ws_bytes} B)"
+        st = bufs["st"][1].view(torch.int32).cpu().numpy()
+        assert st[1] & pkg.STATUS_SHORT and st[4] & pkg.STATUS_SHORT and st[0] == 0 and st[5] == 0
+        pcm = bufs["pcm"][1].view(torch.int16).cpu().numpy()
+        q5 = oden.clean_audio(clips[5])
+        assert np.array_equal(pcm[pcm_starts[5]:pcm_starts[5] + lens[5]], q5)
+
+
 # ---------------------------------------------------------------------------------------------
 # size-independent properties at the bench configuration (BASELINE.json configs 2/3: 10 000 clips)
 # ---------------------------------------------------------------------------------------------
