@@ -227,8 +227,16 @@ def extract_features_host(audio: torch.Tensor, denoise: bool = True, prop_decrea
         base_lens = torch.full((chunk,), n, dtype=torch.int32, device=dev)
         for s in streams:
             s.wait_stream(cur)
-        for ci, c0 in enumerate(range(0, B, chunk)):
-            cnt = min(chunk, B - c0)
+        # ramp-up: the first copies are short so the kernels start early (quarter and half chunks first)
+        bounds, c0 = [], 0
+        for frac in (4, 2):
+            if B - c0 > chunk:
+                bounds.append((c0, max(1, chunk // frac)))
+                c0 += bounds[-1][1]
+        while c0 < B:
+            bounds.append((c0, min(chunk, B - c0)))
+            c0 += bounds[-1][1]
+        for ci, (c0, cnt) in enumerate(bounds):
             s = streams[ci & 1]
             with torch.cuda.stream(s):
                 d_in = staging[ci & 1][:cnt * n]

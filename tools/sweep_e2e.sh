@@ -1,4 +1,4 @@
-for c in 500 1000 1250 2000 2500 5000; do
+for c in 1000 1250 1600 2000; do
   echo "== e2e-chunk $c"
   python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-chunk $c 2>&1 | python -c "
 import sys,json
