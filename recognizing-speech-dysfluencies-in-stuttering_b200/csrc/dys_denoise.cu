@@ -73,22 +73,65 @@ __device__ __forceinline__ NrGeom nr_geom(const ClipView& cv, int item, int cpc)
 }
 
 struct NrTables {
-    double hann[kNrFft];
     double2 tw512[16 * 32];
     double2 tw32h[32];
+};
+// The forward kernel (k_nr_stft_mag) is bound by the FP64 pipe and keeps its window / split factors in tables;
+// the inverse kernel (k_nr_apply_ola) is bound by shared-memory traffic and derives them arithmetically (below).
+struct NrFwdTables {
+    double hann[kNrFft];
     double2 split[512];
 };
 
 __device__ __forceinline__ void nr_load_tables(NrTables& sm, const DeviceTables& tb, int tid, int nthreads) {
-    for (int i = tid; i < kNrFft; i += nthreads) sm.hann[i] = tb.hann1024[i];
-    for (int i = tid; i < 512; i += nthreads) { sm.tw512[i] = tb.tw512[i]; sm.split[i] = tb.split1024[i]; }
+    for (int i = tid; i < 512; i += nthreads) sm.tw512[i] = tb.tw512[i];
     if (tid < 32) sm.tw32h[tid] = tb.tw32h[tid];
+}
+__device__ __forceinline__ void nr_load_fwd_tables(NrFwdTables& sm, const DeviceTables& tb, int tid, int nthreads) {
+    for (int i = tid; i < kNrFft; i += nthreads) sm.hann[i] = tb.hann1024[i];
+    for (int i = tid; i < 512; i += nthreads) sm.split[i] = tb.split1024[i];
+}
+
+// Window and real-split factors without table look-ups (the FFT kernels are bound by shared-memory wavefronts):
+// every lane keeps the sine/cosine of its own base angles and rotates them by compile-time constants,
+//   hann[2 (lane + 32 q) + e] = 0.5 - 0.5 cos(theta_e + q pi/8),   theta_e = 2 pi (2 lane + e) / 1024,
+//   split[lane + 32 q]        = exp(i (psi + q pi/16)),            psi     = 2 pi lane / 1024,
+// one multiply + one fused multiply-add per component, within ~1.5 ulp of the correctly rounded table entry.
+struct LaneTrig {
+    double c0, s0, c1, s1;      // cos / sin of theta_0, theta_1
+    double ck, sk;              // cos / sin of psi
+};
+// Called once per frame: hides the six values from loop-invariant code motion, which would otherwise hoist all
+// 16 + 16 derived factors out of the frame loop and spill them to local memory.
+__device__ __forceinline__ LaneTrig per_frame(LaneTrig t) {
+    asm volatile("" : "+d"(t.c0), "+d"(t.s0), "+d"(t.c1), "+d"(t.s1), "+d"(t.ck), "+d"(t.sk));
+    return t;
+}
+__device__ __forceinline__ LaneTrig lane_trig(const DeviceTables& tb, int lane) {
+    const double2 a = tb.split1024[2 * lane], b = tb.split1024[2 * lane + 1], c = tb.split1024[lane];
+    return LaneTrig{a.x, a.y, b.x, b.y, c.x, c.y};
+}
+// cos / sin of 2 pi i / 64 for 0 <= i < 64
+__host__ __device__ constexpr double kCos64w(int i) { return i <= 32 ? kCos64(i) : kCos64(64 - i); }
+__host__ __device__ constexpr double kSin64w(int i) { return i <= 32 ? kSin64(i) : -kSin64(64 - i); }
+
+template <int Q>
+__device__ __forceinline__ double2 hann_pair(const LaneTrig& t) {
+    constexpr double cq = kCos64w(4 * Q), sq = kSin64w(4 * Q);
+    const double ca = fma(t.c0, cq, -(t.s0 * sq)), cb = fma(t.c1, cq, -(t.s1 * sq));
+    return make_double2(fma(-0.5, ca, 0.5), fma(-0.5, cb, 0.5));
+}
+template <int Q>
+__device__ __forceinline__ double2 split_factor(const LaneTrig& t) {
+    constexpr double cq = kCos64w(2 * Q), sq = kSin64w(2 * Q);
+    return make_double2(fma(t.ck, cq, -(t.sk * sq)), fma(t.sk, cq, t.ck * sq));
 }
 
 // Windowed frame t of the zero-padded chunk -> STFT bins.  On return x[q] = D[lane + 32 q] (q < 16)
 // and *nyq = D[512] (real).
-__device__ __forceinline__ void nr_frame_stft(const NrTables& sm, double2* xbuf, const float* __restrict__ base, bool vec_ok,
-                                              const NrGeom& g, int t, int lane, double2 (&x)[16], double* nyq) {
+__device__ __forceinline__ void nr_frame_stft(const NrTables& sm, const NrFwdTables& fw, double2* xbuf,
+                                              const float* __restrict__ base, bool vec_ok, const NrGeom& g, int t, int lane,
+                                              double2 (&x)[16], double* nyq) {
     double2 v[16];
     const int p0 = t * kNrHop - kNrFft / 2;                 // padded-chunk coordinate of the frame's first sample
     static_for<16>([&](auto im) {
@@ -106,7 +149,7 @@ __device__ __forceinline__ void nr_frame_stft(const NrTables& sm, double2* xbuf,
             if (in0) a = __ldg(base + s);
             if (in1) b = __ldg(base + s + 1);
         }
-        v[m] = make_double2(double(a) * sm.hann[j2], double(b) * sm.hann[j2 + 1]);
+        v[m] = make_double2(double(a) * fw.hann[j2], double(b) * fw.hann[j2 + 1]);
     });
     warp_fft512_rolled(v, xbuf, sm.tw512, sm.tw32h, lane);  // Z[lane + 32 q] = v[bitrev(q, 4)]
     // real split through the (now free) exchange tile: every lane publishes its Z and fetches the partner
@@ -123,7 +166,7 @@ __device__ __forceinline__ void nr_frame_stft(const NrTables& sm, double2* xbuf,
         const double2 z = v[bitrev(q, 4)];
         const double2 p = lds_once(&xbuf[512 - k]);
         const double ex = z.x + p.x, ey = z.y - p.y, dx = z.x - p.x, dy = z.y + p.y;
-        const double2 cs = lds_once(&sm.split[k]);
+        const double2 cs = lds_once(&fw.split[k]);
         x[q] = make_double2(0.5 * (ex + (cs.x * dy - cs.y * dx)), 0.5 * (ey - (cs.x * dx + cs.y * dy)));
     });
     const double2 z0 = xbuf[512];
@@ -134,6 +177,7 @@ __device__ __forceinline__ void nr_frame_stft(const NrTables& sm, double2* xbuf,
 // ------------------------------------------------------------------------------------------
 struct MagSmem {
     NrTables tab;
+    NrFwdTables fwd;
     double2 xbuf[kWarps][kXbuf512];
 };
 
@@ -148,6 +192,7 @@ k_nr_stft_mag(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
     if (t_begin > g.t_last) return;
     const int t_end = min(g.t_last + 1, t_begin + kFramesPerCta);
     nr_load_tables(sm.tab, tb, tid, kThreads);
+    nr_load_fwd_tables(sm.fwd, tb, tid, kThreads);
     __syncthreads();
     const float* base = cv.audio + cv.starts[g.clip];
     const bool vec_ok = (reinterpret_cast<uintptr_t>(base) & 7u) == 0 && (g.c0 & 1) == 0;
@@ -156,7 +201,7 @@ k_nr_stft_mag(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
     for (int t = t_begin + warp; t < t_end; t += kWarps) {
         double2 x[16];
         double nyq;
-        nr_frame_stft(sm.tab, sm.xbuf[warp], base, vec_ok, g, t, lane, x, &nyq);
+        nr_frame_stft(sm.tab, sm.fwd, sm.xbuf[warp], base, vec_ok, g, t, lane, x, &nyq);
         double* row = mag + size_t(t - g.t_first) * kNrBinsPad;
         double2* srow = spec + size_t(t - g.t_first) * kNrBinsPad;
         static_for<16>([&](auto iq) {
@@ -353,6 +398,7 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
     double2* xb = sm.xbuf[warp];
     double* mrow = reinterpret_cast<double*>(xb);
     const double one_minus_prop = 1.0 - prop;
+    const LaneTrig trig = lane_trig(tb, lane);
     float peak = 0.f;
     bool bad = false;
     int cbuf = 0;
@@ -367,6 +413,7 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
             if (lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(trow + 512));
             // the frame's spectrum was stored by k_nr_stft_mag: its 16 + 1 loads are in flight while the mask row is smoothed
             const double2* srow = spec + size_t(t - g.t_first) * kNrBinsPad;
+            const LaneTrig tr = per_frame(trig);
             double2 x[16];
             static_for<16>([&](auto iq) {
                 constexpr int q = decltype(iq)::value;
@@ -431,7 +478,7 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
                 const double2 a = x[q];
                 const double2 p = lds_once(&xb[512 - k]);       // X[512 - k]  (k = 0: the Nyquist bin)
                 const double ex = a.x + p.x, ey = a.y - p.y, dx = a.x - p.x, dy = a.y + p.y;
-                const double2 cs = lds_once(&sm.tab.split[k]);
+                const double2 cs = split_factor<q>(tr);
                 const double zr = ex - (dx * cs.y + dy * cs.x);
                 const double zi = ey + (dx * cs.x - dy * cs.y);
                 v[q] = make_double2(zr, -zi);
@@ -444,7 +491,8 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
                 constexpr int rq = bitrev(q, 4);
                 const int j = lane + 32 * q;
                 const double s0 = v[rq].x * (1.0 / 1024.0), s1 = -v[rq].y * (1.0 / 1024.0);
-                xb[j] = make_double2(s0 * sm.tab.hann[2 * j], s1 * sm.tab.hann[2 * j + 1]);
+                const double2 w = hann_pair<q>(tr);
+                xb[j] = make_double2(s0 * w.x, s1 * w.y);
             });
         } else {
 #pragma unroll
