@@ -434,3 +434,19 @@ def test_cache_artifacts_are_reference_compatible(fe, pkg, synth, tmp_path, monk
         # cache hit: the reference-named loader returns the stored vector without touching the GPU
         np.testing.assert_array_equal(fe.cached_extract_features(p, "", "raw"), raw)
     assert fe.clean_audio_and_cache(paths[0]) == os.path.normpath("clear_audio/clip0.wav")
+    # the reference keys its caches by basename stem only (pipeline1.py:132,432): a second file with the same stem
+    # aliases the first one's WAV and vectors (16 stems of its corpus do); a cached entry is loaded, not recomputed
+    os.makedirs("other")
+    owav.write_wav_pcm16("other/clip1.wav", owav.quantize_pcm16(synth.synth_clip(77, 30000)))
+    np.save("cache_features/clip2_raw_feats.npy", np.full(149, 3.0, np.float32))
+    Xb2, Xa2, kept2 = fe.build_feature_cache(["in/clip0.wav", "in/clip1.wav", "other/clip1.wav", "in/clip2.wav"])
+    assert len(kept2) == 4
+    np.testing.assert_array_equal(Xb2[2], Xb2[1])
+    np.testing.assert_array_equal(Xa2[2], Xa2[1])
+    np.testing.assert_array_equal(Xb2[1], Xb[1])
+    assert np.all(Xb2[3] == 3.0) and np.array_equal(Xa2[3], Xa[2])
+    Xb3, Xa3, _ = fe.build_feature_cache(["other/clip1.wav", "in/clip1.wav"], overwrite=True)    # same stem inside one call
+    np.testing.assert_array_equal(Xb3[0], Xb3[1])
+    np.testing.assert_array_equal(Xa3[0], Xa3[1])
+    assert not np.array_equal(Xb3[0], Xb[1])                  # the first occurrence (other/clip1.wav) owns the entry now
+    np.testing.assert_array_equal(np.load("cache_features/clip1_raw_feats.npy"), Xb3[0])
