@@ -16,6 +16,8 @@ Outputs (committed; /root/reference does not exist on the GPU box):
   tests/golden/ref_classifier_after.npz -- the class label of each of those 905 rows and the accuracy /
       log-loss the reference published for the cleaned features (output_results/metrics_summary.csv):
       the end-to-end golden of the classifier input loader.
+  tests/golden/ref_file_bytes.npz -- the bytes of the smallest committed clear_audio/<stem>.wav and of its
+      cache_features/<stem>_clean_feats.npy: goldens of the two on-disk formats.
 Only data is copied, never reference source code.
 """
 import glob
@@ -86,6 +88,15 @@ def main():
                         models=np.asarray(list(after)), accuracy=np.asarray([after[m][0] for m in after]),
                         test_loss=np.asarray([after[m][1] for m in after]))
     print("classifier golden:", {m: after[m] for m in after})
+
+    # on-disk format golden: the raw bytes of one committed clear_audio WAV (header + samples) and of one
+    # committed cache_features .npy -- what soundfile.write / np.save produced at pipeline1.py:142 / :439
+    small = min(feats, key=lambda f: os.path.getsize(f"{REF}/clear_audio/{os.path.basename(f)[:-len('_clean_feats.npy')]}.wav"))
+    stem = os.path.basename(small)[:-len("_clean_feats.npy")]
+    np.savez_compressed(os.path.join(HERE, "ref_file_bytes.npz"),
+                        wav=np.frombuffer(open(f"{REF}/clear_audio/{stem}.wav", "rb").read(), dtype=np.uint8),
+                        npy=np.frombuffer(open(small, "rb").read(), dtype=np.uint8), stem=np.asarray(stem))
+    print("file-bytes golden:", stem)
 
 
 if __name__ == "__main__":

@@ -98,3 +98,23 @@ def test_wav_io_round_trip(pkg, tmp_path):
     from oracle import wavio as owav
     back, _ = owav.read_wav_pcm16(str(p))
     assert np.array_equal(back, q)
+
+
+def test_on_disk_formats_are_byte_identical_to_the_reference(pkg, golden_dir, tmp_path):
+    """the WAV the package writes for the reference's PCM and the .npy it writes for the reference's
+    vector are byte-for-byte the files the reference committed (soundfile PCM_16 header, np.save v1 header)."""
+    import io
+    g = np.load(os.path.join(golden_dir, "ref_file_bytes.npz"))
+    wav_bytes, npy_bytes = g["wav"].tobytes(), g["npy"].tobytes()
+    src = tmp_path / "ref.wav"
+    src.write_bytes(wav_bytes)
+    y, sr = pkg.wavio.read_wav(str(src))
+    assert sr == 16000 and y.dtype == np.float32
+    pcm = np.round(y * 32768.0).astype(np.int16)
+    out = tmp_path / "ours.wav"
+    pkg.wavio.write_wav_pcm16(str(out), pcm, sr)
+    assert out.read_bytes() == wav_bytes
+    vec = np.load(io.BytesIO(npy_bytes))
+    assert vec.shape == (149,) and vec.dtype == np.float32
+    np.save(tmp_path / "ours.npy", vec)
+    assert (tmp_path / "ours.npy").read_bytes() == npy_bytes and len(npy_bytes) == 724
