@@ -36,8 +36,6 @@ constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kFramesPerCta = 64;
 
-__constant__ double c_smooth_f[kNrFreqTaps];      // noisereduce's frequency smoothing taps (sum 1)
-
 struct NrGeom {
     int clip, n, c0, out_len, L, Tn, t_first, t_last;
     bool valid;
@@ -634,8 +632,6 @@ cudaError_t launch_denoise(const DeviceTables& tb, const ClipView& cv, float* cl
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_nr_apply_ola<kApplyWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  int(sizeof(ApplySmem<kApplyWarps>)));
-        if (e != cudaSuccess) return e;
-        e = cudaMemcpyToSymbol(c_smooth_f, host_tables().smooth_f.data(), sizeof(double) * kNrFreqTaps);
         if (e != cudaSuccess) return e;
         attr_set[dev & 63] = true;
     }

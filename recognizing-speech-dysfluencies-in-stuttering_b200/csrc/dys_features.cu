@@ -5,15 +5,16 @@
 // call chain  feature.mfcc -> melspectrogram -> stft -> power_to_db -> dct,  feature.delta x2,
 // feature.chroma_stft -> estimate_tuning -> piptrack -> filters.chroma.
 //
-//   k_frame_spectra : one warp per STFT frame.  Samples are read once with coalesced 8-byte
-//                     loads (4x frame overlap is served by L1/L2), windowed, transformed by the
-//                     warp-resident 1024-point complex FFT (dys_fft.cuh), split into the 1025-bin
-//                     power spectrum, and -- while the frame is still in shared memory/registers --
-//                     reduced to 128 log-mel values and to the piptrack peak list.
+//   k_frame_spectra : one warp per STFT frame.  The 32 coalesced 8-byte sample loads of a frame
+//                     (PCM-16 on the clean branch: 4-byte) are all in flight at once and land directly
+//                     in the FFT's register layout (4x frame overlap is served by L1/L2); windowed,
+//                     transformed by the warp-resident 1024-point complex FFT (dys_fft.cuh), split into
+//                     the 1025-bin power spectrum, and -- while the frame is still in shared memory /
+//                     registers -- reduced to 128 log-mel values and to the piptrack peak list.
 //   k_tuning        : one CTA per clip: exact median (radix select) of the peak magnitudes,
 //                     100-bin residual histogram, first arg-max  -> tuning index.
-//   k_frame_cepstra : one warp per frame: top-dB clamp + DCT-II (20x128) and the 12x1025 chroma
-//                     projection with the tuning's filterbank + inf-norm.
+//   k_frame_cepstra : one warp per 4 frames (every chroma weight load feeds 4 x 12 FMAs): top-dB clamp +
+//                     DCT-II (20x128) and the 12x1025 chroma projection with the tuning's filterbank + inf-norm.
 //   k_clip_stats    : one CTA per clip: delta / delta-delta (Savitzky-Golay taps, replicated
 //                     edges) and mean / population std of every row -> the 149-vector.
 #include <cfloat>
