@@ -88,10 +88,9 @@ struct SpectraSmem {
     float hann[kNfft];
     float2 tw[32 * 32];
     float2 split[1024];
-    float mel_w[kMelNnz + 4];
+    float mel_wt[kMelWtMax];            // step-major weights (dys_tables.h): conflict-free across the 32 filters of a group
     int mel_start[kMels];
     int mel_len[kMels];
-    int mel_ptr[kMels];
     float2 xbuf[kWarps][kXbuf1024];
 };
 
@@ -110,10 +109,8 @@ k_frame_spectra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
 
     for (int i = tid; i < kNfft; i += kThreads) sm.hann[i] = tb.hann2048[i];
     for (int i = tid; i < 1024; i += kThreads) { sm.tw[i] = tb.tw1024[i]; sm.split[i] = tb.split2048[i]; }
-    for (int i = tid; i < kMelNnz; i += kThreads) sm.mel_w[i] = tb.mel_w[i];
-    for (int i = tid; i < kMels; i += kThreads) {
-        sm.mel_start[i] = tb.mel_start[i]; sm.mel_len[i] = tb.mel_len[i]; sm.mel_ptr[i] = tb.mel_ptr[i];
-    }
+    for (int i = tid; i < tb.mel_wt_len; i += kThreads) sm.mel_wt[i] = tb.mel_wt[i];
+    for (int i = tid; i < kMels; i += kThreads) { sm.mel_start[i] = tb.mel_start[i]; sm.mel_len[i] = tb.mel_len[i]; }
     __syncthreads();
 
     float2* xbuf = sm.xbuf[warp];
@@ -223,10 +220,11 @@ k_frame_spectra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
 #pragma unroll 1
         for (int g = 0; g < 4; ++g) {
             const int f = lane + 32 * g;
-            const int st = sm.mel_start[f], ln = sm.mel_len[f], pt = sm.mel_ptr[f];
+            const int st = sm.mel_start[f], ln = sm.mel_len[f];
+            const float* wt = sm.mel_wt + tb.mel_goff[g] + lane;
             float acc = 0.f;
 #pragma unroll 4
-            for (int j = 0; j < ln; ++j) acc = fmaf(sm.mel_w[pt + j], pbuf[st + j], acc);
+            for (int j = 0; j < ln; ++j) acc = fmaf(wt[32 * j], pbuf[st + j], acc);
             const float L = 10.0f * log10f(fmaxf(acc, 1e-10f));
             gl[f] = L;
             warp_lmax = fmaxf(warp_lmax, L);

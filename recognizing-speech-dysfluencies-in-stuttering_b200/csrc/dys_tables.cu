@@ -9,6 +9,7 @@
 //   noisereduce _smoothing_filter / get_time_smoothed_representation (pipeline1.py:140)
 #include "dys_tables.h"
 
+#include <algorithm>
 #include <cmath>
 #include <mutex>
 
@@ -72,6 +73,19 @@ void build_mel(HostTables& t) {
             for (int k = first; k <= last; ++k) t.mel_w.push_back(t.mel_dense[size_t(i) * kBins + k]);
         }
     }
+}
+
+void build_mel_step_major(HostTables& t) {
+    int off = 0;
+    for (int g = 0; g < 4; ++g) {
+        int L = 0;
+        for (int l = 0; l < 32; ++l) L = std::max(L, t.mel_len[32 * g + l]);
+        t.mel_goff[g] = off;
+        off += 32 * L;
+    }
+    t.mel_wt.assign(size_t(off), 0.f);
+    for (int f = 0; f < kMels; ++f)
+        for (int j = 0; j < t.mel_len[f]; ++j) t.mel_wt[t.mel_goff[f / 32] + 32 * j + f % 32] = t.mel_w[t.mel_ptr[f] + j];
 }
 
 void build_chroma(HostTables& t) {
@@ -158,6 +172,7 @@ void build(HostTables& t) {
         t.split1024[k] = make_double2(std::cos(a), std::sin(a));
     }
     build_mel(t);
+    build_mel_step_major(t);
     // ortho DCT-II rows 0..19 over 128 mel bands
     t.dct.resize(size_t(kMfcc) * kMels);
     for (int k = 0; k < kMfcc; ++k)
@@ -222,10 +237,14 @@ const DeviceTables* device_tables() {
         set_error("mel filterbank has " + std::to_string(h.mel_w.size()) + " non-zeros, expected 2020");
         return nullptr;
     }
+    if (int(h.mel_wt.size()) > kMelWtMax) {
+        set_error("step-major mel table has " + std::to_string(h.mel_wt.size()) + " entries, more than kMelWtMax");
+        return nullptr;
+    }
     DeviceTables d{};
     bool ok = upload(h.hann2048, &d.hann2048) && upload(h.tw1024, &d.tw1024) && upload(h.split2048, &d.split2048) &&
               upload(h.mel_start, &d.mel_start) && upload(h.mel_len, &d.mel_len) && upload(h.mel_ptr, &d.mel_ptr) &&
-              upload(h.mel_w, &d.mel_w) && upload(h.dct, &d.dct) && upload(h.chroma, &d.chroma) &&
+              upload(h.mel_w, &d.mel_w) && upload(h.mel_wt, &d.mel_wt) && upload(h.dct, &d.dct) && upload(h.chroma, &d.chroma) &&
               upload(h.tuning_edges, &d.tuning_edges) && upload(h.hann1024, &d.hann1024) &&
               upload(h.tw512, &d.tw512) && upload(h.tw32h, &d.tw32h) && upload(h.split1024, &d.split1024) &&
               upload(h.wss, &d.wss) && upload(h.smooth_f, &d.smooth_f) && upload(h.smooth_t, &d.smooth_t);
@@ -234,6 +253,8 @@ const DeviceTables* device_tables() {
         return nullptr;
     }
     d.iir_b = h.iir_b;
+    for (int g = 0; g < 4; ++g) d.mel_goff[g] = h.mel_goff[g];
+    d.mel_wt_len = int(h.mel_wt.size());
     g_dev[dev] = d;
     g_dev_ready[dev] = true;
     return &g_dev[dev];

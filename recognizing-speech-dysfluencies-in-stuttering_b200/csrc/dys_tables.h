@@ -20,6 +20,7 @@ constexpr int kChroma = 12;
 constexpr int kFeat = 149;              // pipeline1.py:86 TOTAL_FEATURE_LEN
 constexpr int kAudioFeat = 144;         // pipeline1.py:84 AUDIO_FEATURE_LEN
 constexpr int kMelNnz = 2020;
+constexpr int kMelWtMax = 32 * 88;       // step-major mel weights: 32 x (6 + 10 + 22 + 48) used
 constexpr int kTunings = 100;
 constexpr int kPipLo = 20;              // 150 Hz <= k * 7.8125 < 4000 Hz  ->  k in [20, 511]
 constexpr int kPipHi = 511;
@@ -40,6 +41,10 @@ struct HostTables {
     std::vector<float2> split2048;          // [1024]   (cos, sin)(2 pi k / 2048)
     std::vector<int> mel_start, mel_len, mel_ptr;   // [128]
     std::vector<float> mel_w;               // [2020]
+    // the same weights step-major for the lane-per-filter loop: filter f = lane + 32 g, its j-th bin at
+    // mel_wt[mel_goff[g] + 32 j + lane] -> the 32 simultaneous weight reads are conflict-free
+    std::vector<float> mel_wt;              // [32 * sum_g (longest filter of group g)]
+    int mel_goff[4] = {0, 0, 0, 0};
     std::vector<float> mel_dense;           // [128*1025] (debug / tests only, host side)
     std::vector<float> dct;                 // [20*128]  ortho DCT-II rows
     std::vector<float> chroma;              // [100][1025][12]
@@ -61,6 +66,9 @@ struct DeviceTables {
     const int* mel_len;
     const int* mel_ptr;
     const float* mel_w;
+    const float* mel_wt;
+    int mel_goff[4];
+    int mel_wt_len;
     const float* dct;
     const float* chroma;
     const double* tuning_edges;
