@@ -122,6 +122,9 @@ k_frame_spectra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
     float2* g_peaks = sc.peaks + size_t(li) * sc.t_max * kMaxPeaksPerFrame;
     float warp_lmax = -INFINITY;
     bool nonfinite = false;
+    // The clean branch reads PCM-16 and librosa.load returns int16 / 32768: the FFT runs on the integers (scaling by
+    // a power of two commutes exactly with every rounding on the way) and the 2^-30 lands in the power's 1/4 factor.
+    const float pscale = src.q16 ? 0.25f * (1.0f / 1073741824.0f) : 0.25f;
     const int n = src.n;
 
     for (int t = t_begin + warp; t < t_end; t += kWarps) {
@@ -137,16 +140,14 @@ k_frame_spectra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
             static_for<32>([&](auto im) { constexpr int m = decltype(im)::value; raw[m] = __ldg(q2 + lane + 32 * m); });
             static_for<32>([&](auto im) {
                 constexpr int m = decltype(im)::value;
-                const float2 w = hann2[lane + 32 * m];
-                v[m] = make_float2(float(raw[m].x) * (1.0f / 32768.0f) * w.x, float(raw[m].y) * (1.0f / 32768.0f) * w.y);
+                v[m] = vmul(make_float2(float(raw[m].x), float(raw[m].y)), hann2[lane + 32 * m]);   // x 2^15, undone at the power
             });
         } else if (interior && src.vec_ok) {
             const float2* x2 = reinterpret_cast<const float2*>(src.f32 + f0);
             static_for<32>([&](auto im) { constexpr int m = decltype(im)::value; v[m] = __ldg(x2 + lane + 32 * m); });
             static_for<32>([&](auto im) {
                 constexpr int m = decltype(im)::value;
-                const float2 w = hann2[lane + 32 * m];
-                v[m] = make_float2(v[m].x * w.x, v[m].y * w.y);
+                v[m] = vmul(v[m], hann2[lane + 32 * m]);
             });
         } else {
 #pragma unroll 2
@@ -154,8 +155,8 @@ k_frame_spectra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
                 const int s = f0 + 2 * i;
                 float a = 0.f, b = 0.f;
                 if (src.q16) {
-                    if (s >= 0 && s < n) a = float(__ldg(src.q16 + s)) * (1.0f / 32768.0f);
-                    if (s + 1 >= 0 && s + 1 < n) b = float(__ldg(src.q16 + s + 1)) * (1.0f / 32768.0f);
+                    if (s >= 0 && s < n) a = float(__ldg(src.q16 + s));
+                    if (s + 1 >= 0 && s + 1 < n) b = float(__ldg(src.q16 + s + 1));
                 } else {
                     if (s >= 0 && s < n) a = __ldg(src.f32 + s);
                     if (s + 1 >= 0 && s + 1 < n) b = __ldg(src.f32 + s + 1);
@@ -192,12 +193,13 @@ k_frame_spectra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
             const int k = lane + 32 * q;                    // 0 .. 511
             const float2 z = v[bitrev(q, 5)];
             const float2 p = zb[512 - k];                   // Z[1024 - k]  (k = 0: Z[0])
-            const float ex = z.x + p.x, ey = z.y - p.y, dx = z.x - p.x, dy = z.y + p.y;
+            const float2 pc = make_float2(p.x, -p.y);
+            const float2 e = cadd(z, pc), d = csub(z, pc);  // packed FADD2: (ex, ey) = z + conj p, (dx, dy) = z - conj p
             const float2 cs = sm.split[k];
-            const float tx = cs.x * dy - cs.y * dx, ty = -(cs.x * dx + cs.y * dy);
-            const float ar = ex + tx, ai = ey + ty, br = ex - tx, bi = ey - ty;
-            const float plo = 0.25f * (ar * ar + ai * ai);
-            const float phi = 0.25f * (br * br + bi * bi);
+            const float2 tt = make_float2(cs.x * d.y - cs.y * d.x, -(cs.x * d.x + cs.y * d.y));
+            const float2 a = cadd(e, tt), b = csub(e, tt);
+            const float plo = pscale * (a.x * a.x + a.y * a.y);
+            const float phi = pscale * (b.x * b.x + b.y * b.y);
             fmax_ = fmaxf(fmax_, fmaxf(plo, phi));
             gp[k] = plo;
             gp[1024 - k] = phi;
@@ -206,7 +208,7 @@ k_frame_spectra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
         });
         if (lane == 0) {
             const float2 z = v[bitrev(16, 5)];
-            const float p_mid = z.x * z.x + z.y * z.y;      // X[512] = conj Z[512]
+            const float p_mid = (4.0f * pscale) * (z.x * z.x + z.y * z.y);      // X[512] = conj Z[512]
             gp[512] = p_mid;
             pbuf[512] = p_mid;
             fmax_ = fmaxf(fmax_, p_mid);

@@ -39,12 +39,21 @@ template <> __device__ __forceinline__ float2 cadd<float2>(float2 a, float2 b) {
         : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
     return r;
 }
+// element-wise product (window multiply): one FMUL2
+__device__ __forceinline__ float2 vmul(float2 a, float2 b) {
+    float2 r;
+    asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd; }"
+        : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return r;
+}
 template <> __device__ __forceinline__ float2 csub<float2>(float2 a, float2 b) {
     float2 r;
     asm("{ .reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; sub.rn.f32x2 rd, ra, rb; mov.b64 {%0, %1}, rd; }"
         : "=f"(r.x), "=f"(r.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
     return r;
 }
+#else
+__device__ __forceinline__ float2 vmul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
 #endif
 template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
     C r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r;
