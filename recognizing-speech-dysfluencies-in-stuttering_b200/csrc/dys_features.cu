@@ -431,7 +431,7 @@ k_frame_cepstra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
         const float* gp[kCepFrames];
 #pragma unroll
         for (int f = 0; f < kCepFrames; ++f) gp[f] = g_power + size_t(min(t0 + f, t_end - 1)) * kBinsPad;
-#pragma unroll 2
+#pragma unroll 4
         for (int j = 0; j < 32; ++j) {
             const int k = lane + 32 * j;
             const float4 w0 = __ldg(&wtab[k * 3 + 0]), w1 = __ldg(&wtab[k * 3 + 1]), w2 = __ldg(&wtab[k * 3 + 2]);
