@@ -8,6 +8,8 @@ in scaler.py.
 """
 from __future__ import annotations
 
+import os
+
 
 def shard_range(n_items: int, rank: int, world: int) -> tuple[int, int]:
     if world < 1 or not (0 <= rank < world):
@@ -21,3 +23,35 @@ def sliding_windows(n_samples: int, win: int = 48000, hop: int = 24000):
     if n_samples < win:
         return []
     return list(range(0, n_samples - win + 1, hop))
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Best effort: pin the calling process to the CPUs of the NUMA node its GPU hangs off, so that pinned host
+    staging buffers allocated afterwards are first-touched in memory local to that GPU's PCIe root.  With one
+    process per GPU on a two-socket box this keeps every rank's host-to-device stream on its own socket instead of
+    all eight reading one socket's DRAM (measured: 23 GB/s per GPU unbound at 8 GPUs vs 55 GB/s for one GPU alone).
+    Returns what it did ({"node": n, "cpus": k}) or why it did nothing; never raises."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (getattr(props, "pci_domain_id", 0), props.pci_bus_id, props.pci_device_id)
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return {"skipped": "no NUMA affinity reported for " + bus}
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return {"skipped": f"node {node} has no CPU this process may use"}
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed), "bus": bus}
+    except Exception as e:  # noqa: BLE001 - purely an optimisation
+        return {"skipped": f"{type(e).__name__}: {e}"}
