@@ -204,11 +204,18 @@ def extract_features_batch(audio, lengths=None, starts=None, sr: int = TARGET_SR
 
 
 def extract_features_host(audio: torch.Tensor, denoise: bool = True, prop_decrease: float | None = None,
-                          chunk_clips: int = 2048, out_raw: torch.Tensor | None = None,
-                          out_clean: torch.Tensor | None = None, device=None):
+                          chunk_clips: int = 400, out_raw: torch.Tensor | None = None,
+                          out_clean: torch.Tensor | None = None, device=None, compute_streams: int = 3):
     """End-to-end host path: equal-length clips [B, n] in (preferably pinned) HOST memory ->
-    host float32 [B,149] raw (and clean).  Clips stream to the device in chunks on two CUDA streams
-    so the PCIe copies overlap the kernels; results are copied back into pinned host tensors."""
+    host float32 [B,149] raw (and clean).
+
+    One copy stream pushes the whole batch to the device back to back, chunk by chunk, and records an event per
+    chunk, so the PCIe link is never idle.  ``compute_streams`` compute streams take the chunks in turn: each waits
+    for its chunk's event, runs the kernels on it (own scratch arena) and sends the 2 x 149 floats per clip back into
+    the (pinned) result tensors.  Compute trails the copy by about one chunk, so chunks are small; two streams let a
+    chunk's kernels fill the idle tail of its predecessor's, which is what makes small chunks efficient (measured on
+    B200, 10 000 3-s clips: 42.6 ms with one compute stream and 1250-clip chunks, 39.9 ms with two streams and 625,
+    37.8 ms with three and 400; the copy alone takes 34.5 ms, the kernels alone 34.4 ms)."""
     if audio.is_cuda or audio.dim() != 2 or audio.dtype != torch.float32:
         raise ValueError("audio must be a 2-D float32 CPU tensor [B, n]")
     prop = PROP_DECREASE if prop_decrease is None else float(prop_decrease)
@@ -218,38 +225,48 @@ def extract_features_host(audio: torch.Tensor, denoise: bool = True, prop_decrea
         out_raw = torch.empty((B, FEATURE_LEN), dtype=torch.float32).pin_memory()
     if denoise and out_clean is None:
         out_clean = torch.empty((B, FEATURE_LEN), dtype=torch.float32).pin_memory()
+    if B == 0:
+        return (out_raw, out_clean) if denoise else out_raw
     chunk = max(1, min(int(chunk_clips), B))
+    head = [max(1, chunk // 4), max(1, chunk // 2)] if B >= 3 * chunk else []      # short first copies: kernels start early
+    sizes, left = list(head), B - sum(head)
+    while left > 0:
+        sizes.append(min(chunk, left))
+        left -= sizes[-1]
+    n_comp = max(1, min(int(compute_streams), 4))
     with torch.cuda.device(dev):
         cur = torch.cuda.current_stream(dev)
-        streams = _host_streams(dev)
-        staging = [_arena.get(dev, chunk * n * 4, slot=10 + i).view(torch.float32)[:chunk * n] for i in range(2)]
-        base_starts = (torch.arange(chunk, dtype=torch.int64) * n).to(dev)
-        base_lens = torch.full((chunk,), n, dtype=torch.int32, device=dev)
+        streams = _host_streams(dev, 1 + n_comp)
+        copy_s, comp = streams[0], streams[1:]
+        staging = _arena.get(dev, B * n * 4, slot=10).view(torch.float32)[:B * n]
+        biggest = max(sizes)
+        base_starts = (torch.arange(biggest, dtype=torch.int64) * n).to(dev)
+        base_lens = torch.full((biggest,), n, dtype=torch.int32, device=dev)
         for s in streams:
             s.wait_stream(cur)
-        # ramp-up: the first copies are short so the kernels start early (quarter and half chunks first)
-        bounds, c0 = [], 0
-        for frac in (4, 2):
-            if B - c0 > chunk:
-                bounds.append((c0, max(1, chunk // frac)))
-                c0 += bounds[-1][1]
-        while c0 < B:
-            bounds.append((c0, min(chunk, B - c0)))
-            c0 += bounds[-1][1]
-        for ci, (c0, cnt) in enumerate(bounds):
-            s = streams[ci & 1]
+        landed, c0 = [], 0
+        with torch.cuda.stream(copy_s):
+            for cnt in sizes:
+                staging[c0 * n:(c0 + cnt) * n].copy_(audio[c0:c0 + cnt].reshape(-1), non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_s)
+                landed.append(ev)
+                c0 += cnt
+        c0 = 0
+        for i, (cnt, ev) in enumerate(zip(sizes, landed)):
+            s = comp[i % n_comp]
             with torch.cuda.stream(s):
-                d_in = staging[ci & 1][:cnt * n]
-                d_in.copy_(audio[c0:c0 + cnt].reshape(-1), non_blocking=True)
-                raw, clean, _, _ = _run_device(d_in, base_starts[:cnt], base_lens[:cnt], n, denoise, prop, False, None, 1,
-                                               slot=1 + (ci & 1))
+                s.wait_event(ev)
+                raw, clean, _, _ = _run_device(staging[c0 * n:(c0 + cnt) * n], base_starts[:cnt], base_lens[:cnt], n, denoise,
+                                               prop, False, None, 1, slot=1 + i % n_comp)
                 out_raw[c0:c0 + cnt].copy_(raw, non_blocking=True)
                 if denoise:
                     out_clean[c0:c0 + cnt].copy_(clean, non_blocking=True)
                 raw.record_stream(s)
                 if clean is not None:
                     clean.record_stream(s)
-        for s in streams:
+            c0 += cnt
+        for s in comp:
             cur.wait_stream(s)
         cur.synchronize()
     return (out_raw, out_clean) if denoise else out_raw
@@ -295,11 +312,11 @@ def extract_features_longform(recording, win: int = 48000, hop: int = 24000, den
 _streams: dict = {}
 
 
-def _host_streams(dev: torch.device):
-    key = dev.index
-    if key not in _streams:
-        _streams[key] = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
-    return _streams[key]
+def _host_streams(dev: torch.device, count: int = 2):
+    have = _streams.setdefault(dev.index, [])
+    while len(have) < count:
+        have.append(torch.cuda.Stream(device=dev))
+    return have[:count]
 
 
 # ------------------------------------------------------------------------------------------

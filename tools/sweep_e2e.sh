@@ -1,6 +1,7 @@
-for c in 1000 1250 1600 2000; do
-  echo "== e2e-chunk $c"
-  python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-chunk $c 2>&1 | python -c "
+for cfg in "400 3" "625 3" "400 4" "625 2"; do
+  set -- $cfg
+  echo "== e2e-chunk $1 streams $2"
+  python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-chunk $1 --e2e-streams $2 2>/dev/null | python -c "
 import sys,json
 for ln in sys.stdin:
     if ln.startswith('{'):
