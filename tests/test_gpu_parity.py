@@ -226,6 +226,67 @@ def test_prop_decrease_variants(fe, synth):
     np.testing.assert_allclose(same, y, atol=1e-6)
 
 
+def test_gate_on_hard_dynamics_matches_oracle_pcm(fe, synth):
+    """The IIR kernel keeps only check-points of the forward filter state and re-derives it in reverse during the
+    backward sweep; the cases that stress that (digital silence, 120 dB level jumps, decays over hundreds of frames,
+    clips longer than one check-point interval) must still give the oracle's PCM sample for sample."""
+    rng = np.random.default_rng(7)
+    sr = 16000
+    cases = {}
+    y = synth.synth_clip(500, 5 * sr)
+    y[: sr] = 0.0                                            # 1 s of exact zeros, then speech-like signal
+    y[3 * sr: 3 * sr + 4000] = 0.0                           # a hole of exact zeros in the middle
+    cases["digital_silence"] = y
+    y = (1e-6 * rng.standard_normal(4 * sr)).astype(np.float32)
+    y[2 * sr: 2 * sr + 800] += 0.9 * np.sin(2 * np.pi * 440 * np.arange(800) / sr).astype(np.float32)   # 120 dB burst
+    cases["burst_over_floor"] = y
+    t = np.arange(10 * sr) / sr                              # 10 s: 631 active frames, several check-point intervals
+    cases["long_decay"] = (0.8 * np.exp(-t * 1.2) * np.sin(2 * np.pi * 220 * t) + 1e-4 * rng.standard_normal(t.size)).astype(np.float32)
+    cases["steps"] = np.concatenate([a * rng.standard_normal(sr // 2) for a in (1e-5, 0.3, 1e-4, 0.05, 1e-6, 0.7)]).astype(np.float32)
+    names = list(cases)
+    raw, clean, status, pcm = fe.extract_features_batch([cases[k] for k in names], denoise=True, return_status=True,
+                                                        return_pcm=True)
+    assert not status.any()
+    for i, k in enumerate(names):
+        ref = oden.clean_audio(cases[k])
+        got = pcm[i].cpu().numpy()
+        assert ref is not None and got.shape == ref.shape
+        assert np.array_equal(got, ref), f"{k}: {int((got != ref).sum())} of {ref.size} samples differ"
+        _assert_feature_parity(clean[i].cpu().numpy(), ofeat.extract_features(owav.dequantize_pcm16(ref)), f"clean {k}")
+
+
+def test_random_lengths_and_content_sweep(fe, synth):
+    """Ragged batch of 24 random-length clips (4 096 .. 90 000 samples: 9 .. 176 feature frames, frame counts that
+    are and are not multiples of the kernels' tile sizes) with mixed content: raw features, PCM and clean features
+    against the oracle, clip by clip."""
+    rng = np.random.default_rng(2024)
+    clips = []
+    for i in range(24):
+        n = int(rng.integers(4096, 90001))
+        kind = i % 4
+        if kind == 0:
+            y = synth.synth_clip(700 + i, n)
+        elif kind == 1:
+            y = (rng.uniform(0.01, 0.5) * rng.standard_normal(n)).astype(np.float32)
+        elif kind == 2:
+            t = np.arange(n) / 16000.0
+            f = rng.uniform(100, 3000)
+            y = (0.4 * np.sin(2 * np.pi * f * t) * (0.5 + 0.5 * np.sin(2 * np.pi * 3 * t)) + 0.005 * rng.standard_normal(n)).astype(np.float32)
+        else:
+            y = synth.synth_clip(800 + i, n) * np.float32(rng.uniform(0.05, 1.9))      # includes clipping-level gains
+        clips.append(np.ascontiguousarray(y, dtype=np.float32))
+    raw, clean, status, pcm = fe.extract_features_batch(clips, denoise=True, return_status=True, return_pcm=True)
+    assert not status.any()
+    flips = []
+    for i, y in enumerate(clips):
+        _assert_feature_parity(raw[i].cpu().numpy(), ofeat.extract_features(y), f"raw {i} (n={len(y)})", chroma_flips=flips)
+        q = oden.clean_audio(y)
+        assert np.array_equal(pcm[i].cpu().numpy(), q), f"pcm {i} (n={len(y)})"
+        _assert_feature_parity(clean[i].cpu().numpy(), ofeat.extract_features(owav.dequantize_pcm16(q)),
+                               f"clean {i} (n={len(y)})", chroma_flips=flips)
+    assert len(flips) <= 1, f"tuning-bin disagreements in 48 feature vectors: {flips}"
+
+
 # ---------------------------------------------------------------------------------------------
 # the C ABI called directly (plain pointers + sizes; no host-layer help)
 # ---------------------------------------------------------------------------------------------
