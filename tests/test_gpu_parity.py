@@ -186,6 +186,29 @@ def test_classifier_feed_reproduces_published_metrics(pkg, torch_cuda, golden_di
     np.testing.assert_array_equal(Z2, Z[:5])
 
 
+def test_end_to_end_inference_matches_reference_predictions(fe, pkg, torch_cuda, golden_dir):
+    """BASELINE config 5 in small / main1.py:952-999: WAV -> GPU features -> the training scaler -> the reference's
+    classifier.  For the 24 committed clear_audio WAVs the class probabilities obtained from the GPU features equal
+    (to within two of the 200 trees) the ones obtained from the vectors the reference itself cached for those files."""
+    from sklearn.ensemble import RandomForestClassifier
+    from sklearn.preprocessing import LabelEncoder
+    g = np.load(os.path.join(golden_dir, "ref_scaler_after.npz"))
+    c = np.load(os.path.join(golden_dir, "ref_classifier_after.npz"))
+    pairs = np.load(os.path.join(golden_dir, "ref_clean_pairs.npz"))
+    X = torch_cuda.from_numpy(g["X"]).cuda()
+    Z, sc = pkg.scaler.classifier_inputs(X)                                       # training matrix, as the reference builds it
+    y = LabelEncoder().fit_transform(c["labels"])
+    rf = RandomForestClassifier(n_estimators=200, random_state=42).fit(Z, y)      # main1.py trains on all rows
+    offs = pairs["offsets"]
+    clips = [pairs["pcm"][offs[i]:offs[i + 1]].astype(np.float32) / np.float32(32768.0) for i in range(len(offs) - 1)]
+    feats = fe.extract_features_batch(clips)                                      # librosa.load(wav) -> extract_features
+    Zg, _ = pkg.scaler.classifier_inputs(feats, scaler=sc)
+    Zr, _ = pkg.scaler.classifier_inputs(torch_cuda.from_numpy(pairs["feats"]).cuda(), scaler=sc)
+    pg, pr = rf.predict_proba(Zg), rf.predict_proba(Zr)
+    assert np.array_equal(pg.argmax(1), pr.argmax(1))
+    assert np.abs(pg - pr).max() <= 0.01 + 1e-12                                  # at most two of 200 trees may differ
+
+
 # ---------------------------------------------------------------------------------------------
 # edge cases
 # ---------------------------------------------------------------------------------------------
