@@ -18,6 +18,8 @@ Outputs (committed; /root/reference does not exist on the GPU box):
       the end-to-end golden of the classifier input loader.
   tests/golden/ref_file_bytes.npz -- the bytes of the smallest committed clear_audio/<stem>.wav and of its
       cache_features/<stem>_clean_feats.npy: goldens of the two on-disk formats.
+  tests/golden/ref_qc_after.npz -- snr_after / flat_after / hf_after of output_results/per_file_analysis.csv for
+      the stems of ref_clean_pairs.npz: goldens of the three per-file QC scalars.
 Only data is copied, never reference source code.
 """
 import glob
@@ -57,6 +59,18 @@ def main():
                         offsets=np.asarray(offs, dtype=np.int64), feats=np.stack(gold),
                         names=np.asarray(names))
     print("pairs:", len(picks), "samples:", offs[-1], "lens:", [lens[i] for i in picks])
+
+    # QC golden: the *_after columns of per_file_analysis.csv (pipeline1.py:394-396, computed on the cleaned WAV) for
+    # the picked stems, in the order of ref_clean_pairs.npz
+    import csv as _csv
+    by_stem = {}
+    for r in _csv.DictReader(open(f"{REF}/output_results/per_file_analysis.csv")):
+        by_stem.setdefault(os.path.splitext(r["file"])[0], r)
+    np.savez_compressed(os.path.join(HERE, "ref_qc_after.npz"), names=np.asarray(names),
+                        snr=np.asarray([float(by_stem[s]["snr_after"]) for s in names]),
+                        flat=np.asarray([float(by_stem[s]["flat_after"]) for s in names]),
+                        hf=np.asarray([float(by_stem[s]["hf_after"]) for s in names]))
+    print("qc golden rows:", len(names))
 
     # scaler golden: rows follow sorted(list_audio_files) (pipeline1.py:91-97), key = basename stem
     files = []

@@ -86,6 +86,23 @@ def test_classifier_feed_reproduces_published_metrics(golden_dir):
                                                                     "word repetition"]
 
 
+def test_qc_metrics_match_reference_csv(golden_dir):
+    """snr_db / spectral_flatness_mean / high_freq_energy_ratio (pipeline1.py:151-186) on the committed cleaned WAVs
+    against the *_after columns the reference wrote to per_file_analysis.csv."""
+    from oracle import qc
+    pairs = np.load(os.path.join(golden_dir, "ref_clean_pairs.npz"))
+    gq = np.load(os.path.join(golden_dir, "ref_qc_after.npz"))
+    assert list(gq["names"]) == list(pairs["names"])
+    offs = pairs["offsets"]
+    for i in range(len(offs) - 1):
+        y = wavio.dequantize_pcm16(pairs["pcm"][offs[i]:offs[i + 1]])
+        m = qc.qc_metrics(y)
+        assert abs(m[0] - gq["snr"][i]) < 1e-4, (i, m[0], gq["snr"][i])                 # dB
+        assert abs(m[1] - gq["flat"][i]) <= 5e-4 * gq["flat"][i], (i, m[1], gq["flat"][i])
+        assert abs(m[2] - gq["hf"][i]) <= 1e-5 * gq["hf"][i], (i, m[2], gq["hf"][i])
+    assert qc.snr_db(np.zeros(399, np.float32)) == 0.0 and qc.snr_db(None) == 0.0       # pipeline1.py:155-156
+
+
 def test_wav_round_trip_and_full_scale_property(tmp_path, golden_dir):
     g = np.load(os.path.join(golden_dir, "ref_clean_pairs.npz"))
     offs = g["offsets"]
