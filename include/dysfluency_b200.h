@@ -101,6 +101,14 @@ DYS_API int dys_cmvn_finalize(const double* d_acc, const double* d_shift, double
 DYS_API int dys_cmvn_apply(const float* d_feats, int64_t n_rows, const double* d_mean, const double* d_scale, float* d_out,
                    void* stream);
 
+/* Per-file QC scalars the reference logs to output_results/per_file_analysis.csv       [pipeline1.py:151-186, 379-396]
+ *   d_out float32 [n_clips][3] = { snr_db(y), spectral_flatness_mean(y), high_freq_energy_ratio(y, 16000) }
+ *   (clips shorter than 400 samples: snr 0.0; empty / non-finite clips: flatness 0.0 -- the reference's early return
+ *   and except branches).  Reporting only: the high-frequency ratio evaluates a full-length DFT band per clip. */
+DYS_API int64_t dys_qc_workspace_bytes(int32_t n_clips, int32_t max_len);
+DYS_API int dys_qc_metrics(const float* d_audio, const int64_t* d_starts, const int32_t* d_lengths, int32_t n_clips,
+                           int32_t max_len, float* d_out, void* d_workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- introspection used by the parity tests (stage-wise comparison, SURVEY.md section 4 iii) ---- */
 /* Copies a host-side table: which = 0 mel filterbank float32[128*1025], 1 DCT float32[20*128],
  * 2 chroma filterbank of tuning index `arg` float32[1025*12] ([bin][chroma]), 3 hann2048 float32[2048],

@@ -32,6 +32,8 @@ _SIGNATURES = {
     "dys_cmvn_accumulate": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "dys_cmvn_finalize": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "dys_cmvn_apply": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
+    "dys_qc_workspace_bytes": (_i64, [_i32, _i32]),
+    "dys_qc_metrics": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _vp]),
     "dys_get_table": (_i64, [_i32, _i32, _vp, _i64]),
     "dys_debug_feature_stages": (C.c_int, [_vp, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "dys_debug_denoise": (C.c_int, [_vp, _i32, _f32, _vp, _vp, _vp]),

@@ -214,6 +214,30 @@ DYS_API int dys_cmvn_apply(const float* d_feats, int64_t n_rows, const double* d
     return DYS_OK;
 }
 
+DYS_API int64_t dys_qc_workspace_bytes(int32_t n_clips, int32_t max_len) {
+    if (n_clips < 0 || max_len < 0) return -1;
+    const int n_sub = sub_count(feat_scratch_bytes(1, frames_of(max_len)), feat_cap(), std::max(n_clips, 1));
+    return int64_t(qc_scratch_bytes(n_clips, max_len, n_sub));
+}
+
+DYS_API int dys_qc_metrics(const float* d_audio, const int64_t* d_starts, const int32_t* d_lengths, int32_t n_clips,
+                           int32_t max_len, float* d_out, void* d_workspace, int64_t workspace_bytes, void* stream) {
+    if (int rc = check_common(d_audio, d_starts, d_lengths, n_clips, max_len)) return rc;
+    if (n_clips == 0) return DYS_OK;
+    if (!d_out || !d_workspace) { set_error("null output / workspace pointer"); return DYS_ERR_INVALID; }
+    const DeviceTables* tb = device_tables();
+    if (!tb) return DYS_ERR_CUDA;
+    if (workspace_bytes < dys_qc_workspace_bytes(n_clips, max_len)) {
+        set_error("workspace smaller than dys_qc_workspace_bytes()");
+        return DYS_ERR_WORKSPACE;
+    }
+    const int n_sub = sub_count(feat_scratch_bytes(1, frames_of(max_len)), feat_cap(), n_clips);
+    ClipView cv{};
+    cv.audio = d_audio; cv.starts = d_starts; cv.lengths = d_lengths; cv.n_clips = n_clips; cv.max_len = max_len;
+    DYS_CUDA_OK(launch_qc(*tb, cv, d_out, d_workspace, size_t(workspace_bytes), n_sub, static_cast<cudaStream_t>(stream)));
+    return DYS_OK;
+}
+
 DYS_API int64_t dys_get_table(int32_t which, int32_t arg, void* h_out, int64_t max_elems) {
     const HostTables& h = host_tables();
     const void* src = nullptr;

@@ -95,7 +95,7 @@ struct SpectraSmem {
 };
 
 __global__ void __launch_bounds__(kThreads, 2)
-k_frame_spectra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch sc, int32_t* __restrict__ status) {
+k_frame_spectra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch sc, int32_t* __restrict__ status, int min_frames) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SpectraSmem& sm = *reinterpret_cast<SpectraSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -104,7 +104,7 @@ k_frame_spectra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
     const InstSrc src = inst_source(cv, inst);
     const int T = frames_of(src.n);
     const int t_begin = blockIdx.y * kFramesPerCta;
-    if (T < 9 || t_begin >= T) return;         // short clips emit zeros in k_clip_stats
+    if (T < min_frames || src.n <= 0 || t_begin >= T) return;   // features: short clips (T < 9) emit zeros in k_clip_stats
     const int t_end = min(T, t_begin + kFramesPerCta);
 
     for (int i = tid; i < kNfft; i += kThreads) sm.hann[i] = tb.hann2048[i];
@@ -563,9 +563,7 @@ void feat_scratch_carve(void* base, int n_inst, int t_max, FeatScratch* out) {
     out->t_max = t_max;
 }
 
-cudaError_t launch_features(const DeviceTables& tb, const ClipView& cv, int inst0, int n_inst, const FeatScratch& sc,
-                            float* out_raw, float* out_clean, int32_t* status, cudaStream_t stream) {
-    if (n_inst <= 0) return cudaSuccess;
+static cudaError_t spectra_attr() {
     static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -575,11 +573,31 @@ cudaError_t launch_features(const DeviceTables& tb, const ClipView& cv, int inst
         if (e != cudaSuccess) return e;
         attr_set[dev & 63] = true;
     }
+    return cudaSuccess;
+}
+
+// Power spectrograms only (QC metrics): every clip with at least one sample, however short.
+cudaError_t launch_power_only(const DeviceTables& tb, const ClipView& cv, int inst0, int n_inst, const FeatScratch& sc,
+                              int32_t* status, cudaStream_t stream) {
+    if (n_inst <= 0) return cudaSuccess;
+    if (cudaError_t e = spectra_attr()) return e;
     const int gx = (sc.t_max + kFramesPerCta - 1) / kFramesPerCta;
     { LaunchScope ls(kK_feat_init, stream);
       k_feat_init<<<(n_inst + 255) / 256, 256, 0, stream>>>(sc.peak_count, sc.lmax_enc, status, cv, inst0, n_inst); }
     { LaunchScope ls(kK_frame_spectra, stream);
-      k_frame_spectra<<<dim3(n_inst, gx), kThreads, sizeof(SpectraSmem), stream>>>(tb, cv, inst0, sc, status); }
+      k_frame_spectra<<<dim3(n_inst, gx), kThreads, sizeof(SpectraSmem), stream>>>(tb, cv, inst0, sc, status, 1); }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_features(const DeviceTables& tb, const ClipView& cv, int inst0, int n_inst, const FeatScratch& sc,
+                            float* out_raw, float* out_clean, int32_t* status, cudaStream_t stream) {
+    if (n_inst <= 0) return cudaSuccess;
+    if (cudaError_t e = spectra_attr()) return e;
+    const int gx = (sc.t_max + kFramesPerCta - 1) / kFramesPerCta;
+    { LaunchScope ls(kK_feat_init, stream);
+      k_feat_init<<<(n_inst + 255) / 256, 256, 0, stream>>>(sc.peak_count, sc.lmax_enc, status, cv, inst0, n_inst); }
+    { LaunchScope ls(kK_frame_spectra, stream);
+      k_frame_spectra<<<dim3(n_inst, gx), kThreads, sizeof(SpectraSmem), stream>>>(tb, cv, inst0, sc, status, 9); }
     { LaunchScope ls(kK_tuning, stream);
       k_tuning<<<n_inst, 256, 0, stream>>>(tb, sc); }
     { LaunchScope ls(kK_frame_cepstra, stream);

@@ -52,6 +52,16 @@ void feat_scratch_carve(void* base, int n_inst, int t_max, FeatScratch* out);
 cudaError_t launch_features(const DeviceTables& tb, const ClipView& cv, int inst0, int n_inst, const FeatScratch& sc,
                             float* out_raw, float* out_clean, int32_t* status, cudaStream_t stream);
 
+// k_feat_init + k_frame_spectra only: fills sc.power for every clip with >= 1 sample (QC metrics).
+cudaError_t launch_power_only(const DeviceTables& tb, const ClipView& cv, int inst0, int n_inst, const FeatScratch& sc,
+                              int32_t* status, cudaStream_t stream);
+
+// Per-file QC scalars of the reference (pipeline1.py:151-186): out[n_clips][3] = snr_db, spectral_flatness_mean,
+// high_freq_energy_ratio.  scratch layout is private to dys_qc.cu (qc_scratch_bytes).
+size_t qc_scratch_bytes(int n_clips, int max_len, int n_sub);
+cudaError_t launch_qc(const DeviceTables& tb, const ClipView& cv, float* out, void* scratch, size_t scratch_bytes, int n_sub,
+                      cudaStream_t stream);
+
 // Spectral-gate scratch for a sub-batch of chunks.
 struct NrScratch {
     double* mag;       // [n_items][ta_max][kNrBinsPad]   |STFT|, then (in place) the time-smoothed sigmoid mask

@@ -24,6 +24,11 @@ enum KernelId : int {
     kK_cmvn_merge,
     kK_cmvn_finalize,
     kK_cmvn_apply,
+    kK_qc_snr,
+    kK_qc_hf_bins,
+    kK_qc_finish,
+    kK_qc_flatness,
+    kK_qc_flat_reduce,
     kKernelCount
 };
 

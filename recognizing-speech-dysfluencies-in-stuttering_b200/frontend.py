@@ -9,6 +9,7 @@ Same names, argument meaning and error behaviour as the reference's functions on
     extract_text_features      pipeline1.py:242-254
     extract_features           pipeline1.py:257-265
     cached_extract_features    pipeline1.py:429-440   (a closure there; module-level here)
+    snr_db / spectral_flatness_mean / high_freq_energy_ratio   pipeline1.py:151-186   (QC scalars, reporting only)
 
 plus the batched entry points the reference lacks (``extract_features_batch``,
 ``extract_features_host``, ``extract_features_longform``, ``build_feature_cache``).  PyTorch is only plumbing here: device
@@ -509,6 +510,58 @@ def build_feature_cache(paths: Sequence[str], overwrite: bool = False, io_thread
         for j in jobs:
             j.result()
     return Xb, Xa, kept
+
+
+# ------------------------------------------------------------------------------------------
+# per-file QC scalars (pipeline1.py:151-186; reporting only)
+# ------------------------------------------------------------------------------------------
+def qc_metrics_batch(clips: Sequence, device=None) -> np.ndarray:
+    """float32 [B, 3] = (snr_db, spectral_flatness_mean, high_freq_energy_ratio) of every clip -- the three numbers
+    the reference logs per raw and per cleaned file into output_results/per_file_analysis.csv
+    (pipeline1.py:379-381, 394-396).  ``None`` / empty clips give the reference's fall-back values (0.0)."""
+    lib = _lib.load()
+    dev = _device(device)
+    B = len(clips)
+    if B == 0:
+        return np.zeros((0, 3), dtype=np.float32)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dys_init(), "dys_init")
+        host, h_starts, h_lens, max_len = _pack_host(clips)
+        d_audio = host.to(dev, non_blocking=True)
+        d_starts = torch.from_numpy(h_starts).to(dev, non_blocking=True)
+        d_lens = torch.from_numpy(np.ascontiguousarray(h_lens)).to(dev, non_blocking=True)
+        need = int(lib.dys_qc_workspace_bytes(B, max_len))
+        ws = _arena.get(dev, max(need, 256), slot=5)
+        out = torch.zeros((B, 3), dtype=torch.float32, device=dev)
+        _lib.check(lib.dys_qc_metrics(d_audio.data_ptr(), d_starts.data_ptr(), d_lens.data_ptr(), B, max_len, out.data_ptr(),
+                                      ws.data_ptr(), need, torch.cuda.current_stream(dev).cuda_stream), "dys_qc_metrics")
+        return out.cpu().numpy()
+
+
+def _qc_one(y, column: int) -> float:
+    if y is None:
+        return 0.0
+    y = np.asarray(y, dtype=np.float32).reshape(-1)
+    if y.size == 0:
+        return 0.0
+    return float(qc_metrics_batch([y])[0, column])
+
+
+def snr_db(y) -> float:
+    """pipeline1.py:151-165."""
+    return _qc_one(y, 0)
+
+
+def spectral_flatness_mean(y) -> float:
+    """pipeline1.py:168-174."""
+    return _qc_one(y, 1)
+
+
+def high_freq_energy_ratio(y, sr: int = TARGET_SR) -> float:
+    """pipeline1.py:177-186 (sr must be 16000, like everywhere in this package)."""
+    if sr != TARGET_SR:
+        raise ValueError(f"only sr={TARGET_SR} is supported")
+    return _qc_one(y, 2)
 
 
 # ------------------------------------------------------------------------------------------

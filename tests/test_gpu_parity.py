@@ -16,6 +16,7 @@ import pytest
 from oracle import cmvn as ocmvn
 from oracle import denoise as oden
 from oracle import features as ofeat
+from oracle import qc as oqc
 from oracle import wavio as owav
 
 pytestmark = pytest.mark.gpu
@@ -308,6 +309,35 @@ def test_random_lengths_and_content_sweep(fe, synth):
         _assert_feature_parity(clean[i].cpu().numpy(), ofeat.extract_features(owav.dequantize_pcm16(q)),
                                f"clean {i} (n={len(y)})", chroma_flips=flips)
     assert len(flips) <= 1, f"tuning-bin disagreements in 48 feature vectors: {flips}"
+
+
+def test_qc_metrics_match_oracle_and_reference_csv(fe, synth, golden_dir):
+    """snr_db / spectral_flatness_mean / high_freq_energy_ratio (pipeline1.py:151-186).  Against the
+    oracle on synthetic and edge clips, and against the reference's own per_file_analysis.csv on its committed WAVs.
+    Tolerances: 1e-3 dB, 5e-4 relative (flatness: float32 log-mean), 2e-5 relative (HF ratio: the reference's FFT is
+    float32, the kernel's DFT band float64)."""
+    clips = [synth.synth_clip(i) for i in range(6)] + [c for _, c in synth.edge_clips()]
+    clips += [synth.synth_clip(40, 399), synth.synth_clip(41, 400), synth.synth_clip(42, 33075), synth.synth_clip(43, 1)]
+    got = fe.qc_metrics_batch(clips)
+    assert got.shape == (len(clips), 3) and got.dtype == np.float32
+    for i, y in enumerate(clips):
+        ref = oqc.qc_metrics(y)
+        assert abs(got[i, 0] - ref[0]) < 1e-3, (i, len(y), got[i], ref)
+        assert abs(got[i, 1] - ref[1]) <= 5e-4 * abs(ref[1]) + 1e-9, (i, len(y), got[i], ref)
+        assert abs(got[i, 2] - ref[2]) <= 2e-5 * abs(ref[2]) + 1e-9, (i, len(y), got[i], ref)
+    pairs = np.load(os.path.join(golden_dir, "ref_clean_pairs.npz"))
+    gq = np.load(os.path.join(golden_dir, "ref_qc_after.npz"))
+    offs = pairs["offsets"]
+    wavs = [owav.dequantize_pcm16(pairs["pcm"][offs[i]:offs[i + 1]]) for i in range(len(offs) - 1)]
+    got = fe.qc_metrics_batch(wavs)
+    assert np.abs(got[:, 0] - gq["snr"]).max() < 1e-3
+    assert (np.abs(got[:, 1] - gq["flat"]) <= 5e-4 * gq["flat"]).all()
+    assert (np.abs(got[:, 2] - gq["hf"]) <= 2e-5 * gq["hf"]).all()
+    assert fe.snr_db(None) == 0.0 and fe.spectral_flatness_mean(np.zeros(0, np.float32)) == 0.0
+    assert abs(fe.high_freq_energy_ratio(wavs[3], 16000) - gq["hf"][3]) <= 2e-5 * gq["hf"][3]
+    bad = synth.synth_clip(5).copy()
+    bad[100] = np.nan
+    assert fe.spectral_flatness_mean(bad) == 0.0                                # librosa.stft raises -> except -> 0.0
 
 
 # ---------------------------------------------------------------------------------------------
