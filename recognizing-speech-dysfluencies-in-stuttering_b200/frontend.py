@@ -12,7 +12,7 @@ Same names, argument meaning and error behaviour as the reference's functions on
     snr_db / spectral_flatness_mean / high_freq_energy_ratio   pipeline1.py:151-186   (QC scalars, reporting only)
 
 plus the batched entry points the reference lacks (``extract_features_batch``,
-``extract_features_host``, ``extract_features_longform``, ``build_feature_cache``).  PyTorch is only plumbing here: device
+``extract_features_host``, ``extract_features_longform``, ``build_feature_cache``, ``preprocess_corpus``).  PyTorch is only plumbing here: device
 memory, streams, pinned host buffers.  All arithmetic runs in the CUDA library through its C
 ABI; there is no CPU fallback -- without the built library or a CUDA device calls raise.
 """
@@ -562,6 +562,46 @@ def high_freq_energy_ratio(y, sr: int = TARGET_SR) -> float:
     if sr != TARGET_SR:
         raise ValueError(f"only sr={TARGET_SR} is supported")
     return _qc_one(y, 2)
+
+
+# ------------------------------------------------------------------------------------------
+# the reference's preprocessing + feature loops as one batched pass
+# ------------------------------------------------------------------------------------------
+OUTPUT_DIR = "output_results"            # pipeline1.py:32
+
+
+def preprocess_corpus(paths: Sequence[str], output_dir: str | None = None):
+    """Everything ``run_pipeline`` does up to the feature matrices (pipeline1.py:356-456) in batched GPU passes:
+    per file the QC scalars before and after cleaning, the cleaned WAV in CLEAR_DIR, both cached vectors in
+    CACHE_DIR, ``per_file_analysis.csv`` with the reference's columns, and the label of every kept file (its
+    directory name, pipeline1.py:372).  Unreadable files are skipped like in the reference; a file whose cleaning
+    failed is analysed and featurised from its raw samples (pipeline1.py:385-387).
+    Returns (rows, X_before, X_after, labels, kept_paths); the matrices are what pipeline1.py:455-456 vstacks."""
+    out_dir = OUTPUT_DIR if output_dir is None else output_dir
+    X_before, X_after, kept = build_feature_cache(paths)
+    raw_clips, clean_clips = [], []
+    for p in kept:
+        y, _ = load_audio(p, sr=TARGET_SR)
+        raw_clips.append(y)
+        wav = os.path.normpath(os.path.join(CLEAR_DIR, f"{_stem(p)}.wav"))
+        yc, _ = load_audio(wav, sr=TARGET_SR) if os.path.exists(wav) else (None, None)
+        clean_clips.append(y if yc is None else yc)
+    qb = qc_metrics_batch(raw_clips) if kept else np.zeros((0, 3), np.float32)
+    qa = qc_metrics_batch(clean_clips) if kept else np.zeros((0, 3), np.float32)
+    rows, labels = [], []
+    for i, p in enumerate(kept):
+        label = os.path.basename(os.path.dirname(p)) or "unknown"
+        labels.append(label)
+        rows.append({"file": os.path.basename(p), "label": label, "duration_sec": float(len(raw_clips[i]) / TARGET_SR),
+                     "snr_before_db": float(qb[i, 0]), "snr_after_db": float(qa[i, 0]),
+                     "spectral_flatness_before": float(qb[i, 1]), "spectral_flatness_after": float(qa[i, 1]),
+                     "hf_energy_ratio_before": float(qb[i, 2]), "hf_energy_ratio_after": float(qa[i, 2]),
+                     "transcript": ""})
+    if rows:
+        import pandas as pd
+        os.makedirs(out_dir, exist_ok=True)
+        pd.DataFrame(rows).to_csv(os.path.join(out_dir, "per_file_analysis.csv"), index=False)
+    return rows, X_before, X_after, labels, kept
 
 
 # ------------------------------------------------------------------------------------------

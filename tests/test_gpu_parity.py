@@ -311,6 +311,40 @@ def test_random_lengths_and_content_sweep(fe, synth):
     assert len(flips) <= 1, f"tuning-bin disagreements in 48 feature vectors: {flips}"
 
 
+def test_preprocess_corpus_writes_the_reference_artefacts(fe, synth, tmp_path, monkeypatch):
+    """pipeline1.py:356-456 as one call: per_file_analysis.csv (reference columns), clear_audio/*.wav, cache_features/*.npy,
+    labels from the directory names; every number against the oracle's per-file restatement."""
+    import pandas as pd
+    monkeypatch.chdir(tmp_path)
+    files = []
+    for lab, idx, n in (("word repetition", 60, 30000), ("word repetition", 61, 52000), ("Prolongatio sample", 62, 20480)):
+        os.makedirs(f"segrigated_samples/{lab}", exist_ok=True)
+        p = f"segrigated_samples/{lab}/clip{idx}.wav"
+        owav.write_wav_pcm16(p, owav.quantize_pcm16(synth.synth_clip(idx, n)))
+        files.append(p)
+    rows, Xb, Xa, labels, kept = fe.preprocess_corpus(sorted(files) + ["segrigated_samples/none/missing.wav"])
+    assert kept == sorted(files) and labels == [os.path.basename(os.path.dirname(p)) for p in kept]
+    df = pd.read_csv("output_results/per_file_analysis.csv")
+    assert list(df.columns) == ["file", "label", "duration_sec", "snr_before_db", "snr_after_db", "spectral_flatness_before",
+                                "spectral_flatness_after", "hf_energy_ratio_before", "hf_energy_ratio_after", "transcript"]
+    for i, p in enumerate(kept):
+        y, _ = owav.read_wav_pcm16(p)
+        y = owav.dequantize_pcm16(y)
+        yc = oden.clean_then_load(y)
+        before, after = oqc.qc_metrics(y), oqc.qc_metrics(yc)
+        r = df.iloc[i]
+        assert r["file"] == os.path.basename(p) and abs(r["duration_sec"] - len(y) / 16000) < 1e-12
+        assert abs(r["snr_before_db"] - before[0]) < 1e-3 and abs(r["snr_after_db"] - after[0]) < 1e-3
+        assert abs(r["spectral_flatness_before"] - before[1]) <= 5e-4 * before[1]
+        assert abs(r["spectral_flatness_after"] - after[1]) <= 5e-4 * after[1]
+        assert abs(r["hf_energy_ratio_before"] - before[2]) <= 2e-5 * before[2]
+        assert abs(r["hf_energy_ratio_after"] - after[2]) <= 2e-5 * after[2]
+        _assert_feature_parity(Xb[i], ofeat.extract_features(y), f"X_before {i}")
+        _assert_feature_parity(Xa[i], ofeat.extract_features(yc), f"X_after {i}")
+        stem = os.path.basename(p)[:-4]
+        assert os.path.exists(f"clear_audio/{stem}.wav") and os.path.exists(f"cache_features/{stem}_clean_feats.npy")
+
+
 def test_qc_metrics_match_oracle_and_reference_csv(fe, synth, golden_dir):
     """snr_db / spectral_flatness_mean / high_freq_energy_ratio (pipeline1.py:151-186).  Against the
     oracle on synthetic and edge clips, and against the reference's own per_file_analysis.csv on its committed WAVs.
