@@ -84,33 +84,63 @@ def release_workspaces():
     _arena.clear()
 
 
+def _workspace_limit(dev: torch.device) -> int:
+    """Largest workspace one C-ABI call may ask for: DYS_MAX_WORKSPACE_MB, else half of the free device memory."""
+    env = os.environ.get("DYS_MAX_WORKSPACE_MB")
+    if env:
+        return max(1, int(env)) << 20
+    free, _ = torch.cuda.mem_get_info(dev)
+    return max(free // 2, 1 << 28)
+
+
 def _run_device(d_audio: torch.Tensor, d_starts: torch.Tensor, d_lengths: torch.Tensor, max_len: int, denoise: bool,
                 prop_decrease: float, want_pcm: bool, d_pcm_starts: torch.Tensor | None, total_pcm: int, slot: int = 0,
                 workspace_bytes: int | None = None):
-    """One C-ABI call on the current stream. Returns (raw, clean | None, status, pcm | None) device tensors."""
+    """C-ABI call(s) on the current stream. Returns (raw, clean | None, status, pcm | None) device tensors.
+    The per-clip workspace (denoised float32 + PCM-16 copies) grows with the batch: a batch whose workspace would not
+    fit the limit is run as consecutive pieces over the same arena -- clips are independent, so the rows are the same."""
     lib = _lib.load()
     dev = d_audio.device
     n = int(d_starts.numel())
+    flag = 1 if denoise else 0
     with torch.cuda.device(dev):
         _lib.check(lib.dys_init(), "dys_init")
-        need = lib.dys_workspace_bytes(n, max_len, 1 if denoise else 0) if workspace_bytes is None else workspace_bytes
-        ws = _arena.get(dev, max(int(need), 256), slot)
         stream = torch.cuda.current_stream(dev).cuda_stream
         raw = torch.empty((n, FEATURE_LEN), dtype=torch.float32, device=dev)
-        if not denoise:
-            status = torch.empty((n,), dtype=torch.int32, device=dev)
-            _lib.check(lib.dys_features_raw(d_audio.data_ptr(), d_starts.data_ptr(), d_lengths.data_ptr(), n, max_len,
-                                            raw.data_ptr(), status.data_ptr(), ws.data_ptr(), int(need), stream),
-                       "dys_features_raw")
-            return raw, None, status, None
-        clean = torch.empty((n, FEATURE_LEN), dtype=torch.float32, device=dev)
-        status = torch.empty((2 * n,), dtype=torch.int32, device=dev)
-        pcm = torch.empty((total_pcm,), dtype=torch.int16, device=dev) if want_pcm else None
-        _lib.check(lib.dys_features_raw_clean(d_audio.data_ptr(), d_starts.data_ptr(), d_lengths.data_ptr(), n, max_len,
-                                              float(prop_decrease), raw.data_ptr(), clean.data_ptr(), status.data_ptr(),
-                                              pcm.data_ptr() if want_pcm else None,
-                                              d_pcm_starts.data_ptr() if want_pcm else None, ws.data_ptr(), int(need), stream),
-                   "dys_features_raw_clean")
+        clean = torch.empty((n, FEATURE_LEN), dtype=torch.float32, device=dev) if denoise else None
+        status = torch.empty(((2 if denoise else 1) * n,), dtype=torch.int32, device=dev)
+        pcm = torch.empty((total_pcm,), dtype=torch.int16, device=dev) if (denoise and want_pcm) else None
+        piece = n
+        if workspace_bytes is None and n > 1:
+            limit = _workspace_limit(dev)
+            if lib.dys_workspace_bytes(n, max_len, flag) > limit:
+                lo, hi = 1, n                                   # largest piece whose workspace fits (monotone in the count)
+                while lo < hi:
+                    mid = (lo + hi + 1) // 2
+                    if lib.dys_workspace_bytes(mid, max_len, flag) <= limit:
+                        lo = mid
+                    else:
+                        hi = mid - 1
+                piece = lo
+        need = lib.dys_workspace_bytes(piece, max_len, flag) if workspace_bytes is None else workspace_bytes
+        ws = _arena.get(dev, max(int(need), 256), slot)
+        for i0 in range(0, n, piece):
+            m = min(piece, n - i0)
+            st = status if m == n else torch.empty(((2 if denoise else 1) * m,), dtype=torch.int32, device=dev)
+            if not denoise:
+                _lib.check(lib.dys_features_raw(d_audio.data_ptr(), d_starts[i0:].data_ptr(), d_lengths[i0:].data_ptr(), m,
+                                                max_len, raw[i0:].data_ptr(), st.data_ptr(), ws.data_ptr(), int(need), stream),
+                           "dys_features_raw")
+            else:
+                _lib.check(lib.dys_features_raw_clean(d_audio.data_ptr(), d_starts[i0:].data_ptr(), d_lengths[i0:].data_ptr(), m,
+                                                      max_len, float(prop_decrease), raw[i0:].data_ptr(), clean[i0:].data_ptr(),
+                                                      st.data_ptr(), pcm.data_ptr() if pcm is not None else None,
+                                                      d_pcm_starts[i0:].data_ptr() if pcm is not None else None,
+                                                      ws.data_ptr(), int(need), stream), "dys_features_raw_clean")
+            if m != n:
+                status[i0:i0 + m] = st[:m]
+                if denoise:
+                    status[n + i0:n + i0 + m] = st[m:]
         return raw, clean, status, pcm
 
 

@@ -547,6 +547,18 @@ def test_longform_windows_shard_like_one_gpu(fe, pkg, synth, torch_cuda):
     assert len(s_none) == 0 and r_none.shape == (0, 149) and c_none is None
 
 
+def test_batches_larger_than_the_workspace_limit_run_in_pieces(fe, synth, torch_cuda, monkeypatch):
+    """A batch whose per-clip workspace would not fit is run as consecutive pieces: same rows, status and PCM."""
+    clips = [synth.synth_clip(200 + i, 30000 + 977 * i) for i in range(9)] + [synth.synth_clip(3, 4000)]
+    a = fe.extract_features_batch(clips, denoise=True, return_status=True, return_pcm=True)
+    monkeypatch.setenv("DYS_MAX_WORKSPACE_MB", "12")              # three or four clips per piece
+    b = fe.extract_features_batch(clips, denoise=True, return_status=True, return_pcm=True)
+    assert torch_cuda.equal(a[0], b[0]) and torch_cuda.equal(a[1], b[1]) and torch_cuda.equal(a[2], b[2])
+    assert all(torch_cuda.equal(x, y) for x, y in zip(a[3], b[3]))
+    r = fe.extract_features_batch(clips, denoise=False, return_status=True)
+    assert torch_cuda.equal(r[0], a[0]) and torch_cuda.equal(r[1], a[2][:len(clips)])
+
+
 def test_host_streaming_path_equals_device_path(fe, synth, torch_cuda):
     torch = torch_cuda
     X = torch.from_numpy(synth.synth_batch(40)).pin_memory()
