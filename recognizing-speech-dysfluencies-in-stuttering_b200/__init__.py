@@ -8,12 +8,12 @@ from . import _lib, sharding, synth, wavio  # noqa: F401
 from ._lib import (AUDIO_FEATURE_LEN, FEATURE_LEN, SAMPLE_RATE, STATUS_BAD_LENGTH,  # noqa: F401
                    STATUS_CLEAN_FALLBACK, STATUS_NONFINITE, STATUS_SHORT, DysError)
 
-__all__ = ["frontend", "scaler", "sharding", "synth", "wavio", "DysError", "FEATURE_LEN"]
+__all__ = ["frontend", "scaler", "torch_ops", "sharding", "synth", "wavio", "DysError", "FEATURE_LEN"]
 
 
 def __getattr__(name):
     # torch-dependent modules load lazily so that table/ABI checks stay light
-    if name in ("frontend", "scaler"):
+    if name in ("frontend", "scaler", "torch_ops"):            # torch_ops registers torch.ops.dysb200.*
         import importlib
         return importlib.import_module(f"{__name__}.{name}")
     raise AttributeError(name)

@@ -118,3 +118,22 @@ def test_on_disk_formats_are_byte_identical_to_the_reference(pkg, golden_dir, tm
     assert vec.shape == (149,) and vec.dtype == np.float32
     np.save(tmp_path / "ours.npy", vec)
     assert (tmp_path / "ours.npy").read_bytes() == npy_bytes and len(npy_bytes) == 724
+
+
+def test_torch_operators_are_registered_and_have_no_cpu_kernel(pkg):
+    """The PyTorch-op face of the boundary: torch.ops.dysb200.* exist, infer shapes on fake tensors, and refuse CPU
+    tensors instead of falling back."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    pkg.torch_ops                                                   # registers the operators
+    for name in ("features_raw", "features_raw_clean", "qc_metrics"):
+        assert hasattr(torch.ops.dysb200, name)
+    with FakeTensorMode():
+        a = torch.empty(1000, device="cuda")
+        s = torch.empty(4, dtype=torch.int64, device="cuda")
+        ln = torch.empty(4, dtype=torch.int32, device="cuda")
+        raw, clean, st = torch.ops.dysb200.features_raw_clean(a, s, ln, 250, 1.0)
+        assert raw.shape == clean.shape == (4, 149) and st.shape == (8,) and st.dtype == torch.int32
+        assert torch.ops.dysb200.qc_metrics(a, s, ln, 250).shape == (4, 3)
+    with pytest.raises((NotImplementedError, RuntimeError)):
+        torch.ops.dysb200.features_raw(torch.zeros(10), torch.zeros(1, dtype=torch.int64), torch.ones(1, dtype=torch.int32), 10)

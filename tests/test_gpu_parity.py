@@ -559,6 +559,23 @@ def test_batches_larger_than_the_workspace_limit_run_in_pieces(fe, synth, torch_
     assert torch_cuda.equal(r[0], a[0]) and torch_cuda.equal(r[1], a[2][:len(clips)])
 
 
+def test_torch_operators_equal_the_host_layer(fe, pkg, synth, torch_cuda):
+    """torch.ops.dysb200.* (the registered PyTorch operators over the packed device layout) == extract_features_batch."""
+    torch = torch_cuda
+    pkg.torch_ops
+    X = torch.from_numpy(synth.synth_batch(5)).cuda()
+    n, L = X.shape
+    starts = torch.arange(n, dtype=torch.int64, device="cuda") * L
+    lens = torch.full((n,), L, dtype=torch.int32, device="cuda")
+    raw, clean, st = torch.ops.dysb200.features_raw_clean(X.reshape(-1), starts, lens, L, 1.0)
+    ref_raw, ref_clean, ref_st = fe.extract_features_batch(X, denoise=True, return_status=True)
+    assert torch.equal(raw, ref_raw) and torch.equal(clean, ref_clean) and torch.equal(st, ref_st)
+    r2, s2 = torch.ops.dysb200.features_raw(X.reshape(-1), starts, lens, L)
+    assert torch.equal(r2, ref_raw) and torch.equal(s2, ref_st[:n])
+    qc = torch.ops.dysb200.qc_metrics(X.reshape(-1), starts, lens, L)
+    np.testing.assert_array_equal(qc.cpu().numpy(), fe.qc_metrics_batch(list(X.cpu().numpy())))
+
+
 def test_host_streaming_path_equals_device_path(fe, synth, torch_cuda):
     torch = torch_cuda
     X = torch.from_numpy(synth.synth_batch(40)).pin_memory()
