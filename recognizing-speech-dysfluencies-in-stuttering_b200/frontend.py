@@ -28,8 +28,7 @@ import numpy as np
 import torch
 
 from . import _lib, wavio
-from ._lib import (AUDIO_FEATURE_LEN, FEATURE_LEN, SAMPLE_RATE, STATUS_BAD_LENGTH, STATUS_CLEAN_FALLBACK,
-                   STATUS_NONFINITE, STATUS_SHORT, DysError)
+from ._lib import AUDIO_FEATURE_LEN, FEATURE_LEN, SAMPLE_RATE, STATUS_CLEAN_FALLBACK, DysError
 
 # same module-level knobs as the reference (pipeline1.py:29-32, 77-86)
 CACHE_DIR = "cache_features"

@@ -1,7 +1,7 @@
 """Timeline probe of the host streaming path: when does each chunk's copy land and when is its compute done?"""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 import dysb200 as pkg
 fe = pkg.frontend
 N, L = 10000, 48000

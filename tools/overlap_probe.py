@@ -1,8 +1,8 @@
 """Probe: does running two half-batches concurrently on two streams (their gate and feature phases interleave on
 the SMs) beat one full batch?  Device-resident inputs, CUDA events.  Informs the sub-batch scheduling only."""
-import os, sys, time
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 import dysb200 as pkg
 fe = pkg.frontend
 N, L = 10000, 48000
