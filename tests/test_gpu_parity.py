@@ -576,6 +576,27 @@ def test_torch_operators_equal_the_host_layer(fe, pkg, synth, torch_cuda):
     np.testing.assert_array_equal(qc.cpu().numpy(), fe.qc_metrics_batch(list(X.cpu().numpy())))
 
 
+def test_ragged_batches_run_in_length_bins_with_identical_rows(fe, synth, torch_cuda):
+    """a ragged batch is processed in length-sorted bins (one call per bin, rows scattered back); the rows,
+    status flags and PCM equal the single-call result bit for bit."""
+    torch = torch_cuda
+    rng = np.random.default_rng(11)
+    lens = np.clip((rng.lognormal(np.log(2.0), 0.6, 300) * 16000).astype(int), 3000, 150000)
+    base = synth.synth_clip(1, 150000)
+    clips = [np.ascontiguousarray(base[:n] * np.float32(0.5 + 0.001 * i)) for i, n in enumerate(lens)]
+    a = fe.extract_features_batch(clips, denoise=True, return_status=True, return_pcm=True)          # binned (300 >= 256, ragged)
+    host, h_starts, h_lens, max_len = fe._pack_host(clips)
+    d_audio = host.cuda()
+    pl = np.maximum(h_lens.astype(np.int64), 0)
+    hp = np.zeros(len(clips), np.int64)
+    hp[1:] = np.cumsum(pl)[:-1]
+    raw, clean, st, pcm = fe._run_device(d_audio, torch.from_numpy(h_starts).cuda(), torch.from_numpy(h_lens).cuda(), max_len, True,
+                                         1.0, True, torch.from_numpy(hp).cuda(), int(pl.sum()))     # one call, one max_len
+    assert torch.equal(a[0], raw) and torch.equal(a[1], clean) and torch.equal(a[2], st)
+    assert torch.equal(torch.cat(a[3]), pcm)
+    assert int((st[:300] & 1).sum()) == int((lens < 4096).sum())                                    # short clips flagged
+
+
 def test_host_streaming_path_equals_device_path(fe, synth, torch_cuda):
     torch = torch_cuda
     X = torch.from_numpy(synth.synth_batch(40)).pin_memory()
