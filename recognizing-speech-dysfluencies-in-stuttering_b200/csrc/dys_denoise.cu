@@ -197,6 +197,10 @@ k_nr_stft_mag(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
     double* mag = sc.mag + size_t(li) * sc.ta_max * kNrBinsPad;
     double2* spec = sc.spec + size_t(li) * sc.ta_max * kNrBinsPad;
     for (int t = t_begin + warp; t < t_end; t += kWarps) {
+        {   // this warp's next frame starts 2048 samples further on: pull its 32 lines towards L2 while this one is transformed
+            const long long s_next = (long long)(t + kWarps) * kNrHop - kNrFft / 2 - kNrPad + g.c0 + 32 * lane;
+            if (t + kWarps < t_end && s_next >= 0 && s_next < g.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + s_next));
+        }
         double2 x[16];
         double nyq;
         nr_frame_stft(sm.tab, sm.fwd, sm.xbuf[warp], base, vec_ok, g, t, lane, x, &nyq);

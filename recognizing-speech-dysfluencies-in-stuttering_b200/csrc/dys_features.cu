@@ -133,6 +133,16 @@ k_frame_spectra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
         // overlap the zero centre padding or the clip end take the bounds-checked loop through shared memory.
         const int f0 = t * kHop - kNfft / 2;               // clip-relative index of the frame's first sample
         const bool interior = f0 >= 0 && f0 + kNfft <= n;
+        if (t + kWarps < t_end) {                           // this warp's next frame: pull its lines towards L2 now
+            const int s_next = f0 + kWarps * kHop + 64 * lane;          // 64 samples: 256 B of float32, 128 B of PCM-16
+            if (s_next >= 0 && s_next < n) {
+                if (src.q16) asm volatile("prefetch.global.L2 [%0];" ::"l"(src.q16 + s_next));
+                else {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(src.f32 + s_next));
+                    if (s_next + 32 < n) asm volatile("prefetch.global.L2 [%0];" ::"l"(src.f32 + s_next + 32));
+                }
+            }
+        }
         float2 v[32];
         if (interior && src.q16) {                          // clean branch: int16 / 32768 (exact), as librosa.load reads the WAV
             const short2* q2 = reinterpret_cast<const short2*>(src.q16 + f0);
