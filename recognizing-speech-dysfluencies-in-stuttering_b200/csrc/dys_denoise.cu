@@ -628,17 +628,8 @@ cudaError_t launch_clean_init(const ClipView& cv, float* clean_peak, int32_t* cl
 cudaError_t launch_denoise(const DeviceTables& tb, const ClipView& cv, float* clean, float* clean_peak, int32_t* clean_flag,
                            int cpc, int item0, int n_items, const NrScratch& sc, float prop_decrease, cudaStream_t stream) {
     if (n_items <= 0) return cudaSuccess;
-    static bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attr_set[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(k_nr_stft_mag, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(MagSmem)));
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(k_nr_apply_ola<kApplyWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 int(sizeof(ApplySmem<kApplyWarps>)));
-        if (e != cudaSuccess) return e;
-        attr_set[dev & 63] = true;
-    }
+    if (cudaError_t e = ensure_dynamic_smem<kK_nr_stft_mag>(k_nr_stft_mag, int(sizeof(MagSmem)))) return e;
+    if (cudaError_t e = ensure_dynamic_smem<kK_nr_apply_ola>(k_nr_apply_ola<kApplyWarps>, int(sizeof(ApplySmem<kApplyWarps>)))) return e;
     if (sc.ta_max > kIirMaxCk << kIirCkShift) return cudaErrorInvalidValue;
     const int gy = (sc.ta_max + kFramesPerCta - 1) / kFramesPerCta;
     ClipView cvw = cv;

@@ -573,18 +573,7 @@ void feat_scratch_carve(void* base, int n_inst, int t_max, FeatScratch* out) {
     out->t_max = t_max;
 }
 
-static cudaError_t spectra_attr() {
-    static bool attr_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (!attr_set[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(k_frame_spectra, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             int(sizeof(SpectraSmem)));
-        if (e != cudaSuccess) return e;
-        attr_set[dev & 63] = true;
-    }
-    return cudaSuccess;
-}
+static cudaError_t spectra_attr() { return ensure_dynamic_smem<kK_frame_spectra>(k_frame_spectra, int(sizeof(SpectraSmem))); }
 
 // Power spectrograms only (QC metrics): every clip with at least one sample, however short.
 cudaError_t launch_power_only(const DeviceTables& tb, const ClipView& cv, int inst0, int n_inst, const FeatScratch& sc,

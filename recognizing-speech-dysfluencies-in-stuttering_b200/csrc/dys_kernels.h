@@ -6,7 +6,25 @@
 
 #include "dys_tables.h"
 
+#include <atomic>
+
 namespace dys {
+
+// Opt a kernel into more than 48 KB of dynamic shared memory, once per device; safe to call from several host
+// threads (the attribute call is idempotent, the flag only saves the driver round trip).  Tag = one id per kernel
+// (the flags are per instantiation, and two kernels may share a signature).
+template <int Tag, typename Kernel>
+inline cudaError_t ensure_dynamic_smem(Kernel kernel, int bytes) {
+    static std::atomic<bool> done[64] = {};
+    int dev = 0;
+    if (cudaError_t e = cudaGetDevice(&dev)) return e;
+    std::atomic<bool>& flag = done[dev & 63];
+    if (!flag.load(std::memory_order_acquire)) {
+        if (cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)) return e;
+        flag.store(true, std::memory_order_release);
+    }
+    return cudaSuccess;
+}
 
 // status bits written per clip instance (mirrors the reference's "log + zeros / None" conventions)
 constexpr int kStatusShort = 1;       // T < 9 frames: librosa.feature.delta raises -> zeros(144)   (pipeline1.py:237-239)
