@@ -111,7 +111,9 @@ def _run_device(d_audio: torch.Tensor, d_starts: torch.Tensor, d_lengths: torch.
         pcm = pcm_out if pcm_out is not None else (
             torch.empty((total_pcm,), dtype=torch.int16, device=dev) if (denoise and want_pcm) else None)
         piece = n
-        if workspace_bytes is None and n > 1:
+        # cudaMemGetInfo is a slow, occasionally blocking driver query: only ask when the workspace is big enough to matter
+        # (the 400-clip chunks of the host streaming path never are)
+        if workspace_bytes is None and n > 1 and lib.dys_workspace_bytes(n, max_len, flag) > (1 << 30):
             limit = _workspace_limit(dev)
             if lib.dys_workspace_bytes(n, max_len, flag) > limit:
                 lo, hi = 1, n                                   # largest piece whose workspace fits (monotone in the count)
@@ -300,7 +302,10 @@ def extract_features_host(audio: torch.Tensor, denoise: bool = True, prop_decrea
         sizes.append(min(chunk, left))
         left -= sizes[-1]
     n_comp = max(1, min(int(compute_streams), 4))
+    lib = _lib.load()
+    flag = 1 if denoise else 0
     with torch.cuda.device(dev):
+        _lib.check(lib.dys_init(), "dys_init")
         cur = torch.cuda.current_stream(dev)
         streams = _host_streams(dev, 1 + n_comp)
         copy_s, comp = streams[0], streams[1:]
@@ -308,6 +313,17 @@ def extract_features_host(audio: torch.Tensor, denoise: bool = True, prop_decrea
         biggest = max(sizes)
         base_starts = (torch.arange(biggest, dtype=torch.int64) * n).to(dev)
         base_lens = torch.full((biggest,), n, dtype=torch.int32, device=dev)
+        # per compute stream: its own scratch arena and result rows, allocated once per call -- the per-chunk host work is
+        # then one library call and two result copies (the host thread is the part of this path that a busy box delays)
+        need = int(lib.dys_workspace_bytes(biggest, n, flag))
+        slots = []
+        for k in range(n_comp):
+            ws = _arena.get(dev, max(need, 256), slot=1 + k)
+            rows = _arena.get(dev, biggest * (2 * FEATURE_LEN * 4 + 8), slot=20 + k)
+            raw_k = rows[:biggest * FEATURE_LEN * 4].view(torch.float32).view(biggest, FEATURE_LEN)
+            clean_k = rows[biggest * FEATURE_LEN * 4:2 * biggest * FEATURE_LEN * 4].view(torch.float32).view(biggest, FEATURE_LEN)
+            st_k = rows[2 * biggest * FEATURE_LEN * 4:].view(torch.int32)
+            slots.append((ws, raw_k, clean_k, st_k))
         for s in streams:
             s.wait_stream(cur)
         landed, c0 = [], 0
@@ -319,18 +335,23 @@ def extract_features_host(audio: torch.Tensor, denoise: bool = True, prop_decrea
                 landed.append(ev)
                 c0 += cnt
         c0 = 0
+        in_ptr, st_ptr, ln_ptr = staging.data_ptr(), base_starts.data_ptr(), base_lens.data_ptr()
         for i, (cnt, ev) in enumerate(zip(sizes, landed)):
             s = comp[i % n_comp]
+            ws, raw_k, clean_k, st_k = slots[i % n_comp]
             with torch.cuda.stream(s):
                 s.wait_event(ev)
-                raw, clean, _, _ = _run_device(staging[c0 * n:(c0 + cnt) * n], base_starts[:cnt], base_lens[:cnt], n, denoise,
-                                               prop, False, None, 1, slot=1 + i % n_comp)
-                out_raw[c0:c0 + cnt].copy_(raw, non_blocking=True)
                 if denoise:
-                    out_clean[c0:c0 + cnt].copy_(clean, non_blocking=True)
-                raw.record_stream(s)
-                if clean is not None:
-                    clean.record_stream(s)
+                    rc = lib.dys_features_raw_clean(in_ptr + c0 * n * 4, st_ptr, ln_ptr, cnt, n, prop, raw_k.data_ptr(),
+                                                    clean_k.data_ptr(), st_k.data_ptr(), None, None, ws.data_ptr(), need,
+                                                    s.cuda_stream)
+                else:
+                    rc = lib.dys_features_raw(in_ptr + c0 * n * 4, st_ptr, ln_ptr, cnt, n, raw_k.data_ptr(), st_k.data_ptr(),
+                                              ws.data_ptr(), need, s.cuda_stream)
+                _lib.check(rc, "dys_features_raw_clean" if denoise else "dys_features_raw")
+                out_raw[c0:c0 + cnt].copy_(raw_k[:cnt], non_blocking=True)
+                if denoise:
+                    out_clean[c0:c0 + cnt].copy_(clean_k[:cnt], non_blocking=True)
             c0 += cnt
         for s in comp:
             cur.wait_stream(s)
