@@ -71,6 +71,10 @@ class _Arena:
             self._bufs[key] = buf
         return buf
 
+    def size(self, device: torch.device, slot: int = 0) -> int:
+        buf = self._bufs.get((device.index, slot))
+        return 0 if buf is None else int(buf.numel())
+
     def clear(self):
         self._bufs.clear()
 
@@ -113,9 +117,10 @@ def _run_device(d_audio: torch.Tensor, d_starts: torch.Tensor, d_lengths: torch.
         piece = n
         # cudaMemGetInfo is a slow, occasionally blocking driver query: only ask when the workspace is big enough to matter
         # (the 400-clip chunks of the host streaming path never are)
-        if workspace_bytes is None and n > 1 and lib.dys_workspace_bytes(n, max_len, flag) > (1 << 30):
-            limit = _workspace_limit(dev)
-            if lib.dys_workspace_bytes(n, max_len, flag) > limit:
+        full = lib.dys_workspace_bytes(n, max_len, flag)
+        if workspace_bytes is None and n > 1 and full > (1 << 30) and _arena.size(dev, slot) < full:
+            limit = _workspace_limit(dev)                       # only when a larger arena would have to be allocated
+            if full > limit:
                 lo, hi = 1, n                                   # largest piece whose workspace fits (monotone in the count)
                 while lo < hi:
                     mid = (lo + hi + 1) // 2
