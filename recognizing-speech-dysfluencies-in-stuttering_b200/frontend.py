@@ -151,6 +151,23 @@ def _run_device(d_audio: torch.Tensor, d_starts: torch.Tensor, d_lengths: torch.
         return raw, clean, status, pcm
 
 
+_uniform_cache: dict = {}
+
+
+def _uniform_index(dev: torch.device, B: int, n: int):
+    """starts / lengths of a [B, n] batch, kept on the device (two pageable host-to-device copies per call otherwise:
+    they would make the host wait for everything queued on the stream before)."""
+    key = (dev.index, B, n)
+    hit = _uniform_cache.get(key)
+    if hit is None:
+        if len(_uniform_cache) > 16:
+            _uniform_cache.clear()
+        hit = ((torch.arange(B, dtype=torch.int64, device=dev) * n), torch.full((B,), n, dtype=torch.int32, device=dev))
+        torch.cuda.current_stream(dev).synchronize()             # later calls may run on other streams
+        _uniform_cache[key] = hit
+    return hit
+
+
 def _run_length_binned(d_audio, d_starts, d_lens, h_lens: np.ndarray, denoise: bool, prop: float, want_pcm: bool,
                        d_pcm_starts, total_pcm: int, bins: int = 1):
     """Ragged batches in length-sorted order: clips of similar length then share launch groups and
@@ -251,8 +268,12 @@ def extract_features_batch(audio, lengths=None, starts=None, sr: int = TARGET_SR
             empty = torch.zeros((0, FEATURE_LEN), dtype=torch.float32, device=dev)
             res = (empty, empty.clone()) if denoise else empty
             return res
-        d_starts = torch.from_numpy(h_starts).to(dev, non_blocking=True)
-        d_lens = torch.from_numpy(np.ascontiguousarray(h_lens)).to(dev, non_blocking=True)
+        uniform = (not isinstance(audio, (list, tuple))) and t.dim() == 2 and lengths is None
+        if uniform:                                               # [B, n] batches: the index tensors are cached on the device
+            d_starts, d_lens = _uniform_index(dev, B, max_len)
+        else:
+            d_starts = torch.from_numpy(h_starts).to(dev, non_blocking=True)
+            d_lens = torch.from_numpy(np.ascontiguousarray(h_lens)).to(dev, non_blocking=True)
         pcm_starts = None
         total_pcm = 0
         if denoise and return_pcm:
