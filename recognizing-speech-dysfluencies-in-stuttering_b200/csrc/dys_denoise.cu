@@ -22,6 +22,7 @@
 // Only frames that overlap the un-padded samples are touched (191 of 422 for a 3-s clip).
 #include <algorithm>
 #include <cfloat>
+#include <climits>
 #include <cmath>
 
 #include "dys_fft.cuh"
@@ -72,7 +73,6 @@ __device__ __forceinline__ NrGeom nr_geom(const ClipView& cv, int item, int cpc)
 
 struct NrTables {
     double2 tw512[16 * 32];
-    double2 tw32h[32];
 };
 // The forward kernel (k_nr_stft_mag) is bound by the FP64 pipe and keeps its window / split factors in tables;
 // the inverse kernel (k_nr_apply_ola) is bound by shared-memory traffic and derives them arithmetically (below).
@@ -83,7 +83,6 @@ struct NrFwdTables {
 
 __device__ __forceinline__ void nr_load_tables(NrTables& sm, const DeviceTables& tb, int tid, int nthreads) {
     for (int i = tid; i < 512; i += nthreads) sm.tw512[i] = tb.tw512[i];
-    if (tid < 32) sm.tw32h[tid] = tb.tw32h[tid];
 }
 __device__ __forceinline__ void nr_load_fwd_tables(NrFwdTables& sm, const DeviceTables& tb, int tid, int nthreads) {
     for (int i = tid; i < kNrFft; i += nthreads) sm.hann[i] = tb.hann1024[i];
@@ -149,7 +148,7 @@ __device__ __forceinline__ void nr_frame_stft(const NrTables& sm, const NrFwdTab
         }
         v[m] = make_double2(double(a) * fw.hann[j2], double(b) * fw.hann[j2 + 1]);
     });
-    warp_fft512_rolled(v, xbuf, sm.tw512, sm.tw32h, lane);  // Z[lane + 32 q] = v[bitrev(q, 4)]
+    warp_fft512_rolled(v, xbuf, sm.tw512, lane);  // Z[lane + 32 q] = v[bitrev(q, 4)]
     // real split through the (now free) exchange tile: every lane publishes its Z and fetches the partner
     // Z[512 - k] of each of its bins, so X[k] replaces Z[k] in place (no second register array, no shuffles).
     static_for<16>([&](auto iq) {
@@ -353,19 +352,17 @@ k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
 }
 
 // ------------------------------------------------------------------------------------------
-// Mask row layout in shared memory: bin k (-16 <= k <= 528) at index k + floor(k / 16) + 17, i.e. one
-// pad slot per 16 bins, so that lanes reading 16-bin segments at stride 17 doubles do not collide.
-__device__ __forceinline__ int mrow_idx(int k) { return k + (k >> 4) + 17; }
+// Mask row layout in the warp's tile: bin k (-16 <= k <= 527) at double 18 (floor(k / 16) + 1) + k mod 16.
+__device__ __forceinline__ int seg_idx(int k) { return ((k >> 4) + 1) * 18 + (k & 15); }
 
-// Per-warp tile: FFT exchange (8448 B), then mask row in (579 doubles) + smoothed mask out (545 doubles), then the
-// windowed output frame (8192 B).
+// Per-warp tile: mask row / first running sum / smoothed mask (34 segments of 18 doubles, 4896 B), then the FFT
+// exchange (8448 B), then the windowed output frame (8192 B).
 constexpr int kApplyTile = 576;                        // double2 units = 9216 B
-constexpr int kMaskOutOff = 580;                       // doubles
 
 template <int W>
 struct ApplySmem {
     NrTables tab;
-    double wss[kNrHop];
+    double wss[kNrHop];                                // 1 / window-sum-square
     double carry[(W * 32) / kNrHop][3][kNrHop];        // double-buffered only when two thread groups share it
     float red[W];
     int bad;
@@ -391,7 +388,7 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
     if (hb > h_last) return;
     const int he = min(h_last + 1, hb + blocks_per_cta);      // exclusive
     nr_load_tables(sm.tab, tb, tid, kT);
-    for (int i = tid; i < kNrHop; i += kT) sm.wss[i] = tb.wss[i];
+    for (int i = tid; i < kNrHop; i += kT) sm.wss[i] = 1.0 / tb.wss[i];     // one reciprocal per CTA and sample phase
     if (tid == 0) sm.bad = 0;
     __syncthreads();
     const double* tsm = sc.mag + size_t(li) * sc.ta_max * kNrBinsPad;
@@ -409,61 +406,120 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
     for (int T0 = hb - 1; T0 - 2 < he; T0 += W) {
         const int t = T0 + warp;
         if (t >= g.t_first && t <= g.t_last && t <= he + 1) {
-            // the mask row is needed after the forward FFT: start pulling its 33 lines into L1 now
             const double* trow = tsm + size_t(t - g.t_first) * kNrBinsPad;
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(trow + 16 * lane));
-            if (lane == 0) asm volatile("prefetch.global.L1 [%0];" ::"l"(trow + 512));
-            // the frame's spectrum was stored by k_nr_stft_mag: its 16 + 1 loads are in flight while the mask row is smoothed
             const double2* srow = spec + size_t(t - g.t_first) * kNrBinsPad;
             const LaneTrig tr = per_frame(trig);
+            if (t + W <= g.t_last && t + W <= he + 1) {         // this warp's next frame: pull both rows towards L2
+                const char* nm = reinterpret_cast<const char*>(trow + size_t(W) * kNrBinsPad);
+                const char* ns = reinterpret_cast<const char*>(srow + size_t(W) * kNrBinsPad);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(nm + 128 * lane));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ns + 128 * lane));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(ns + 4096 + 128 * lane));
+                if (lane == 0) {
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(nm + 4096));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(ns + 8192));
+                }
+            }
+            // ---- 33-tap frequency smoothing of the time-smoothed mask row ----------------------------
+            // noisereduce's normalised triangle tri(16) is box17 (*) box17 / 289.  Lane L owns bins 16 L .. 16 L + 15
+            // and runs both 17-bin running sums in registers; a pass needs 8 bins of halo on either side, which
+            // come through the warp's tile (segment s = bins 16 s .. 16 s + 15 at doubles 18 (s + 1) .. : the two
+            // pad slots keep 16-byte accesses of neighbouring lanes in different bank groups).  Every shared-memory
+            // access moves 16 bytes: 230 wavefronts per frame against 324 for the scalar sliding window it replaces.
+            // (Mask values lie in [0, 1]; the running sums stay within ~1e-15 of the direct sums.)
+            double* rb = mrow;
+            const double gain = prop * (1.0 / 289.0);
+            {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int k = 2 * lane + 64 * j;
+                    const double2 v = __ldg(reinterpret_cast<const double2*>(trow + k));
+                    *reinterpret_cast<double2*>(rb + seg_idx(k)) = v;
+                }
+                if (lane < 12) {                                // bins 512 .. 527 (only 512 is data) and the zero halo -8 .. -1
+                    const int k = lane < 8 ? 512 + 2 * lane : 2 * (lane - 8) - 8;
+                    const double v0 = lane == 0 ? __ldg(trow + 512) : 0.0;
+                    *reinterpret_cast<double2*>(rb + seg_idx(k)) = make_double2(v0, 0.0);
+                }
+            }
+            __syncwarp();
+            double b1[16];                                      // first running sum: B1[16 L + i] = sum of bins -8 .. +8 around it
+            {
+                double w[32];                                   // w[i] = mask bin 16 L - 8 + i
+                const double* wl = rb + 18 * lane;
+                static_for<16>([&](auto ic) {
+                    constexpr int c = decltype(ic)::value;
+                    constexpr int off = c < 4 ? 8 + 2 * c : (c < 12 ? 18 + 2 * (c - 4) : 36 + 2 * (c - 12));
+                    const double2 v = lds_once(reinterpret_cast<const double2*>(wl + off));
+                    w[2 * c] = v.x; w[2 * c + 1] = v.y;
+                });
+                double s_ = w[0];
+#pragma unroll
+                for (int j = 1; j <= 16; ++j) s_ += w[j];
+                b1[0] = s_;
+#pragma unroll
+                for (int i = 0; i < 15; ++i) { s_ += w[i + 17] - w[i]; b1[i + 1] = s_; }      // one addition on the serial chain
+                __syncwarp();                                   // every lane holds its window: the tile is free for B1
+                double* own = rb + 18 * (lane + 1);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) *reinterpret_cast<double2*>(own + 2 * c) = make_double2(b1[2 * c], b1[2 * c + 1]);
+                if (lane == 0) {                                // B1[-1 - u] = B1[-u] - m[8 - u]  (bins below 0 are zero)
+                    double e = b1[0], bl[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { e -= w[16 - u]; bl[u] = e; }
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) *reinterpret_cast<double2*>(rb + 8 + 2 * c) = make_double2(bl[7 - 2 * c], bl[6 - 2 * c]);
+                }
+                if (lane == 31) {                               // B1[512 + u] = B1[511 + u] - m[503 + u]  (bins above 512 are zero)
+                    double e = b1[15], br[10];
+#pragma unroll
+                    for (int u = 0; u < 9; ++u) { e -= w[15 + u]; br[u] = e; }
+                    br[9] = 0.0;
+#pragma unroll
+                    for (int c = 0; c < 5; ++c) *reinterpret_cast<double2*>(rb + 18 * 33 + 2 * c) = make_double2(br[2 * c], br[2 * c + 1]);
+                }
+            }
+            __syncwarp();
+            {
+                double B[33];                                   // B[i] = B1[16 L - 8 + i]
+                static_for<4>([&](auto ic) {
+                    constexpr int c = decltype(ic)::value;
+                    const double2 l = lds_once(reinterpret_cast<const double2*>(rb + 18 * lane + 8 + 2 * c));
+                    const double2 r = lds_once(reinterpret_cast<const double2*>(rb + 18 * (lane + 2) + 2 * c));
+                    B[2 * c] = l.x; B[2 * c + 1] = l.y;
+                    B[24 + 2 * c] = r.x; B[25 + 2 * c] = r.y;
+                });
+                B[32] = rb[18 * (lane + 2) + 8];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) B[8 + i] = b1[i];
+                __syncwarp();                                   // halos are in registers: the tile is free for the smoothed mask
+                double o = B[0];
+#pragma unroll
+                for (int j = 1; j <= 16; ++j) o += B[j];
+                double* own = rb + 18 * (lane + 1);
+                double prev_out = 0.0;
+#pragma unroll
+                for (int i = 0; i <= 16; ++i) {
+                    const double val = o * gain + one_minus_prop;      // smoothed bin 16 L + i
+                    if (i & 1) *reinterpret_cast<double2*>(own + i - 1) = make_double2(prev_out, val);
+                    else if (i == 16) { if (lane == 31) own[16 + 2] = val; }   // bin 512 -> segment 32, slot 0
+                    prev_out = val;
+                    if (i < 16) o += B[i + 17] - B[i];
+                }
+            }
+            __syncwarp();
             double2 x[16];
             static_for<16>([&](auto iq) {
                 constexpr int q = decltype(iq)::value;
                 x[q] = __ldg(srow + lane + 32 * q);
             });
             double nyq = __ldg(&srow[512].x);
-            // ---- time-smoothed mask row -> shared (zero halo: 'same' convolution) ------------------
-#pragma unroll
-            for (int j = 0; j < 18; ++j) {
-                const int k = lane - 16 + 32 * j;
-                if (k <= 528) mrow[mrow_idx(k)] = (k >= 0 && k < kNrBins) ? trow[k] : 0.0;
-            }
-            __syncwarp();
-            // ---- 33-tap frequency smoothing, 16 consecutive bins per lane (+ bin 512 on lane 31) ----
-            // noisereduce's normalised triangle tri(16) is box17 (*) box17 / 289: two cascaded 17-bin running sums,
-            // b = B1(k + 8) leading and tr = B1(k - 9) trailing, 6 additions per output instead of 33 multiply-adds.
-            // (mask values lie in [0, 1]; the running sums stay within ~1e-15 of the direct sum.)
-            double* seg = mrow + 17 * lane + 17;                // bin 16 lane + m at seg[m + floor(m / 16)]
-            auto in = [&](int m) { return seg[m + (m >= 0 ? m / 16 : -1)]; };
-            const double gain = prop * (1.0 / 289.0);
-            double* mout = mrow + kMaskOutOff + 17 * lane;      // smoothed bin k at mrow[kMaskOutOff + k + floor(k / 16)]
-            {
-                double b = in(-16);
-#pragma unroll
-                for (int m = -15; m <= 0; ++m) b += in(m);      // B1(-8)
-                double tr = b, o = b;
-#pragma unroll
-                for (int j = -7; j <= 8; ++j) { b = (b + in(j + 8)) - in(j - 9); o += b; }
-                mout[0] = o * gain + one_minus_prop;            // o = sum of B1(-8 .. 8)
-#pragma unroll
-                for (int k = 1; k <= 16; ++k) {
-                    b = (b + in(k + 16)) - in(k - 1);           // B1(k + 8)
-                    o = (o + b) - tr;
-                    if (k < 16) {
-                        mout[k] = o * gain + one_minus_prop;
-                        tr = (tr + in(k)) - in(k - 17);         // B1(k - 8)
-                    } else if (lane == 31) {
-                        mout[17] = o * gain + one_minus_prop;   // bin 512
-                    }
-                }
-            }
-            __syncwarp();
             static_for<16>([&](auto iq) {
                 constexpr int q = decltype(iq)::value;
-                const double mk_ = mrow[kMaskOutOff - 17 + mrow_idx(lane + 32 * q)];
+                const double mk_ = rb[18 * ((lane >> 4) + 2 * q + 1) + (lane & 15)];
                 x[q].x *= mk_; x[q].y *= mk_;
             });
-            nyq *= mrow[kMaskOutOff - 17 + mrow_idx(512)];
+            nyq *= rb[18 * 33];
             // inverse real split: Z'[k] = (X[k] + conj X[512-k]) + i e^{+2 pi i k/1024} (X[k] - conj X[512-k]);
             // the inverse FFT is taken as conj(FFT(conj Z')), overall scale 1/1024.
             __syncwarp();
@@ -486,7 +542,7 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
                 v[q] = make_double2(zr, -zi);
             });
             __syncwarp();
-            warp_fft512_rolled(v, xb, sm.tab.tw512, sm.tab.tw32h, lane);
+            warp_fft512_rolled(v, xb, sm.tab.tw512, lane);
             // windowed frame -> this warp's tile (sample 2 j, 2 j + 1 at double2 index j)
             static_for<16>([&](auto iq) {
                 constexpr int q = decltype(iq)::value;
@@ -518,7 +574,9 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
                 if (h < hb || h >= he) continue;
                 const int s_local = h * kNrHop + j - kNrPad;
                 if (s_local >= 0 && s_local < g.out_len) {
-                    const float y = float(acc / sm.wss[j]);
+                    // librosa's istft divides by the window-sum-square in float64; multiplying by its correctly rounded
+                    // reciprocal differs by at most one float64 ulp before the float32 rounding
+                    const float y = float(acc * sm.wss[j]);
                     out[s_local] = y;
                     if (isfinite(y)) peak = fmaxf(peak, fabsf(y)); else bad = true;
                 }
@@ -642,9 +700,17 @@ cudaError_t launch_denoise(const DeviceTables& tb, const ClipView& cv, float* cl
     // output blocks of 256 samples per chunk, split evenly over CTAs of about 16 W frames
     const int max_out = std::min(cv.max_len, kNrChunk);
     const int n_blocks = (kNrPad + std::max(max_out, 1) - 1) / kNrHop - kNrPad / kNrHop + 1;
-    const int per_cta_target = 8 * kApplyWarps - 3;
-    const int n_cta = (n_blocks + per_cta_target - 1) / per_cta_target;
-    const int blocks_per_cta = (n_blocks + n_cta - 1) / n_cta;
+    // A CTA that owns b blocks transforms b + 3 frames in rounds of kApplyWarps: pick the rounds per CTA (4..12) that
+    // leave the fewest idle warp slots over the whole chunk (a 3-s clip: 188 blocks -> 61 + 61 + 61 + 5 = 25 rounds;
+    // the even split 4 x 47 ran 28).
+    int blocks_per_cta = kApplyWarps * 8 - 3, best_rounds = INT_MAX;
+    for (int r : {8, 7, 9, 6, 10, 5, 11, 12, 4}) {
+        const int bpc = kApplyWarps * r - 3;
+        const int full = (n_blocks - 1) / bpc, last = n_blocks - full * bpc;
+        const int rounds = full * r + (last + 3 + kApplyWarps - 1) / kApplyWarps;
+        if (rounds < best_rounds) { best_rounds = rounds; blocks_per_cta = bpc; }
+    }
+    const int n_cta = (n_blocks + blocks_per_cta - 1) / blocks_per_cta;
     { LaunchScope ls(kK_nr_apply_ola, stream);
       k_nr_apply_ola<kApplyWarps><<<dim3(n_items, n_cta), kApplyWarps * 32, sizeof(ApplySmem<kApplyWarps>), stream>>>(
           tb, cvw, cpc, item0, sc, double(prop_decrease), blocks_per_cta, clean, clean_peak, clean_flag); }

@@ -368,7 +368,19 @@ k_tuning(const DeviceTables tb, FeatScratch sc) {
 }
 
 // ------------------------------------------------------------------------------------------
-constexpr int kCepFrames = 4;           // frames per warp iteration: every chroma weight load feeds 4 x 12 FMAs
+#ifndef DYS_CEP_UNROLL
+#define DYS_CEP_UNROLL 2
+#endif
+#ifndef DYS_CEP_PREFETCH
+#define DYS_CEP_PREFETCH 1
+#endif
+#ifndef DYS_CEP_FRAMES
+#define DYS_CEP_FRAMES 6
+#endif
+// frames per warp iteration: every chroma weight load feeds kCepFrames x 12 FMAs (8 warps x 6 frames: a 94-frame clip
+// takes two balanced iterations)
+constexpr int kCepFrames = DYS_CEP_FRAMES;
+constexpr int kCepUnroll = DYS_CEP_UNROLL;     // bins-per-lane steps unrolled in the chroma projection
 
 struct CepstraSmem {
     float dctT[kMels * kMfcc];          // [m][k]
@@ -382,7 +394,7 @@ __device__ __forceinline__ void chroma_fma(float (&acc)[kChroma], float p, const
     acc[9] = fmaf(w2.y, p, acc[9]); acc[10] = fmaf(w2.z, p, acc[10]); acc[11] = fmaf(w2.w, p, acc[11]);
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_frame_cepstra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch sc) {
     __shared__ CepstraSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -398,7 +410,8 @@ k_frame_cepstra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
     }
     __syncthreads();
     const float thr = dec_f32(sc.lmax_enc[li]) - 80.0f;                 // power_to_db top_db over the WHOLE clip
-    const float4* wtab = reinterpret_cast<const float4*>(tb.chroma + size_t(sc.tuning_idx[li]) * kBins * kChroma);
+    const float4* wtab = tb.chroma + size_t(sc.tuning_idx[li]) * 3 * kChromaPitch;        // planes of chroma rows 0-3, 4-7, 8-11
+#define DYS_W3(k) __ldg(&wtab[k]), w1 = __ldg(&wtab[kChromaPitch + (k)]), w2 = __ldg(&wtab[2 * kChromaPitch + (k)])
     const float* g_power = sc.power + size_t(li) * sc.t_max * kBinsPad;
     const float* g_logmel = sc.logmel + size_t(li) * sc.t_max * kMels;
     float* g_mfcc = sc.mfcc + size_t(li) * sc.t_max * kMfcc;
@@ -407,7 +420,7 @@ k_frame_cepstra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
 
     for (int t0 = t_begin + warp * kCepFrames; t0 < t_end; t0 += kWarps * kCepFrames) {
         const int nf = min(kCepFrames, t_end - t0);                      // warp-uniform
-        // ---- clamp + DCT-II: lane k < 20 owns coefficient k of the 4 frames ----------------------
+        // ---- clamp + DCT-II: lane k < 20 owns coefficient k of the warp's frames ----------------------
 #pragma unroll
         for (int f = 0; f < kCepFrames; ++f) {
             const int tt = min(t0 + f, t_end - 1);
@@ -416,43 +429,52 @@ k_frame_cepstra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
         }
         __syncwarp();
         if (lane < kMfcc) {
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
+            float a[kCepFrames];
+#pragma unroll
+            for (int f = 0; f < kCepFrames; ++f) a[f] = 0.f;
+#pragma unroll 2
             for (int m4 = 0; m4 < kMels / 4; ++m4) {
-                const float4 l0 = lrow[0][m4], l1 = lrow[1][m4], l2 = lrow[2][m4], l3 = lrow[3][m4];
                 const float d0 = sm.dctT[(4 * m4 + 0) * kMfcc + lane], d1 = sm.dctT[(4 * m4 + 1) * kMfcc + lane];
                 const float d2 = sm.dctT[(4 * m4 + 2) * kMfcc + lane], d3 = sm.dctT[(4 * m4 + 3) * kMfcc + lane];
-                a0 = fmaf(l0.x, d0, a0); a0 = fmaf(l0.y, d1, a0); a0 = fmaf(l0.z, d2, a0); a0 = fmaf(l0.w, d3, a0);
-                a1 = fmaf(l1.x, d0, a1); a1 = fmaf(l1.y, d1, a1); a1 = fmaf(l1.z, d2, a1); a1 = fmaf(l1.w, d3, a1);
-                a2 = fmaf(l2.x, d0, a2); a2 = fmaf(l2.y, d1, a2); a2 = fmaf(l2.z, d2, a2); a2 = fmaf(l2.w, d3, a2);
-                a3 = fmaf(l3.x, d0, a3); a3 = fmaf(l3.y, d1, a3); a3 = fmaf(l3.z, d2, a3); a3 = fmaf(l3.w, d3, a3);
+#pragma unroll
+                for (int f = 0; f < kCepFrames; ++f) {
+                    const float4 l = lrow[f][m4];
+                    a[f] = fmaf(l.x, d0, a[f]); a[f] = fmaf(l.y, d1, a[f]); a[f] = fmaf(l.z, d2, a[f]); a[f] = fmaf(l.w, d3, a[f]);
+                }
             }
-            g_mfcc[size_t(t0) * kMfcc + lane] = a0;
-            if (nf > 1) g_mfcc[size_t(t0 + 1) * kMfcc + lane] = a1;
-            if (nf > 2) g_mfcc[size_t(t0 + 2) * kMfcc + lane] = a2;
-            if (nf > 3) g_mfcc[size_t(t0 + 3) * kMfcc + lane] = a3;
+#pragma unroll
+            for (int f = 0; f < kCepFrames; ++f)
+                if (f < nf) g_mfcc[size_t(t0 + f) * kMfcc + lane] = a[f];
         }
-        // ---- chroma: 12 x 1025 projection of 4 frames, lane owns bins lane + 32 j -----------------
+        // ---- chroma: 12 x 1025 projection of the warp's frames, lane owns bins lane + 32 j -----------------
         float acc[kCepFrames][kChroma];
 #pragma unroll
         for (int f = 0; f < kCepFrames; ++f)
 #pragma unroll
             for (int c = 0; c < kChroma; ++c) acc[f][c] = 0.f;
-        const float* gp[kCepFrames];
+#if DYS_CEP_PREFETCH
+        {   // the warp's power rows are contiguous (kCepFrames x 4128 B, straight from DRAM): ask for all of their lines
+            // now, so that the projection loop below finds them in L2 (it keeps only a few loads per lane in flight)
+            const char* blk = reinterpret_cast<const char*>(g_power + size_t(t0) * kBinsPad);
+            const int bytes = nf * kBinsPad * 4;
+            for (int o = 128 * lane; o < bytes; o += 128 * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(blk + o));
+        }
+#endif
+        int go[kCepFrames];                                              // row offsets (frames past the end repeat the last row)
 #pragma unroll
-        for (int f = 0; f < kCepFrames; ++f) gp[f] = g_power + size_t(min(t0 + f, t_end - 1)) * kBinsPad;
-#pragma unroll 4
+        for (int f = 0; f < kCepFrames; ++f) go[f] = min(t0 + f, t_end - 1) * kBinsPad + lane;
+#pragma unroll kCepUnroll
         for (int j = 0; j < 32; ++j) {
             const int k = lane + 32 * j;
-            const float4 w0 = __ldg(&wtab[k * 3 + 0]), w1 = __ldg(&wtab[k * 3 + 1]), w2 = __ldg(&wtab[k * 3 + 2]);
+            const float4 w0 = DYS_W3(k);
 #pragma unroll
-            for (int f = 0; f < kCepFrames; ++f) chroma_fma(acc[f], gp[f][k], w0, w1, w2);
+            for (int f = 0; f < kCepFrames; ++f) chroma_fma(acc[f], g_power[go[f] + 32 * j], w0, w1, w2);
         }
         if (lane == 0) {
             const int k = 1024;
-            const float4 w0 = __ldg(&wtab[k * 3 + 0]), w1 = __ldg(&wtab[k * 3 + 1]), w2 = __ldg(&wtab[k * 3 + 2]);
+            const float4 w0 = DYS_W3(k);
 #pragma unroll
-            for (int f = 0; f < kCepFrames; ++f) chroma_fma(acc[f], gp[f][k], w0, w1, w2);
+            for (int f = 0; f < kCepFrames; ++f) chroma_fma(acc[f], g_power[go[f] + k], w0, w1, w2);
         }
 #pragma unroll
         for (int f = 0; f < kCepFrames; ++f) {

@@ -176,11 +176,10 @@ __device__ __forceinline__ void warp_fft1024_rolled(float2 (&v)[32], float2* xbu
 
 // ---- 512-point complex FFT, fp64, one warp -------------------------------------------------
 // in : v[m] = z[lane + 32 m], m < 16   out: Z[lane + 32 q] = v[bitrev(q, 4)], q < 16
-// xbuf: 16x33 double2 private to the warp; tw512[kA*32 + l] = W_512^(l*kA);
-// tw32h[h*16 + l'] = (h ? W_32^l' : 1).  16-point pass, exchange + radix-2 combine across half-warps, 16-point pass
-// (one rolled copy of the butterfly code).
-__device__ __forceinline__ void warp_fft512_rolled(double2 (&v)[16], double2* xbuf, const double2* __restrict__ tw512,
-                                                   const double2* __restrict__ tw32h, int lane) {
+// xbuf: 16x33 double2 private to the warp; tw512[kA*32 + l] = W_512^(l*kA).
+// 16-point pass, exchange + radix-2 combine across half-warps (upper half * W_32^l', a compile-time constant), 16-point
+// pass (one rolled copy of the butterfly code).
+__device__ __forceinline__ void warp_fft512_rolled(double2 (&v)[16], double2* xbuf, const double2* __restrict__ tw512, int lane) {
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
         fft_reg<16, double>(v);
@@ -200,7 +199,12 @@ __device__ __forceinline__ void warp_fft512_rolled(double2 (&v)[16], double2* xb
                 const double2 a = xbuf[kA * 33 + l];
                 const double2 b = xbuf[kA * 33 + l + 16];
                 double2 d = mk<double>(a.x + sgn * b.x, a.y + sgn * b.y);
-                if constexpr (l != 0) d = cmul(d, tw32h[h * 16 + l]);
+                // upper half-warp: * W_32^l (a compile-time constant); lower: * 1.  Register selects instead of a
+                // 16-byte shared-memory load whose 32 lanes fetch only two distinct values (4 wavefronts each).
+                if constexpr (l != 0) {
+                    const double c = h ? kCos64(2 * l) : 1.0, s = h ? -kSin64(2 * l) : 0.0;
+                    d = mk<double>(d.x * c - d.y * s, d.x * s + d.y * c);
+                }
                 v[l] = d;
             });
             __syncwarp();

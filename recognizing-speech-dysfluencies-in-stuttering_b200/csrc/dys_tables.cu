@@ -160,12 +160,6 @@ void build(HostTables& t) {
             const double a = 2.0 * kPi * ((l * kA) % 512) / 512.0;
             t.tw512[kA * 32 + l] = make_double2(std::cos(a), -std::sin(a));
         }
-    t.tw32h.resize(32);
-    for (int l = 0; l < 16; ++l) {
-        const double a = 2.0 * kPi * l / 32.0;
-        t.tw32h[l] = make_double2(1.0, 0.0);
-        t.tw32h[16 + l] = make_double2(std::cos(a), -std::sin(a));
-    }
     t.split1024.resize(512);
     for (int k = 0; k < 512; ++k) {
         const double a = 2.0 * kPi * k / 1024.0;
@@ -182,6 +176,11 @@ void build(HostTables& t) {
             t.dct[size_t(k) * kMels + m] = float(c);
         }
     build_chroma(t);
+    t.chroma_planes.assign(size_t(kTunings) * 3 * kChromaPitch * 4, 0.f);
+    for (int ti = 0; ti < kTunings; ++ti)
+        for (int k = 0; k < kBins; ++k)
+            for (int c = 0; c < kChroma; ++c)
+                t.chroma_planes[((size_t(ti) * 3 + c / 4) * kChromaPitch + k) * 4 + c % 4] = t.chroma[(size_t(ti) * kBins + k) * kChroma + c];
     // istft normaliser in the interior: four squared-window taps added in ascending frame order
     t.wss.resize(kNrHop);
     for (int p = 0; p < kNrHop; ++p) {
@@ -209,6 +208,15 @@ bool upload(const std::vector<T>& h, const T** d) {
     if (cudaMalloc(&p, h.size() * sizeof(T)) != cudaSuccess) return false;
     if (cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) return false;
     *d = p;
+    return true;
+}
+
+// uploads a float vector that the device reads through a wider vector type
+template <typename V>
+bool upload_as(const std::vector<float>& h, const V** d) {
+    const float* p = nullptr;
+    if (!upload(h, &p)) return false;
+    *d = reinterpret_cast<const V*>(p);                      // cudaMalloc returns 256-byte aligned memory
     return true;
 }
 
@@ -244,9 +252,9 @@ const DeviceTables* device_tables() {
     DeviceTables d{};
     bool ok = upload(h.hann2048, &d.hann2048) && upload(h.tw1024, &d.tw1024) && upload(h.split2048, &d.split2048) &&
               upload(h.mel_start, &d.mel_start) && upload(h.mel_len, &d.mel_len) && upload(h.mel_ptr, &d.mel_ptr) &&
-              upload(h.mel_w, &d.mel_w) && upload(h.mel_wt, &d.mel_wt) && upload(h.dct, &d.dct) && upload(h.chroma, &d.chroma) &&
+              upload(h.mel_w, &d.mel_w) && upload(h.mel_wt, &d.mel_wt) && upload(h.dct, &d.dct) && upload_as(h.chroma_planes, &d.chroma) &&
               upload(h.tuning_edges, &d.tuning_edges) && upload(h.hann1024, &d.hann1024) &&
-              upload(h.tw512, &d.tw512) && upload(h.tw32h, &d.tw32h) && upload(h.split1024, &d.split1024) &&
+              upload(h.tw512, &d.tw512) && upload(h.split1024, &d.split1024) &&
               upload(h.wss, &d.wss) && upload(h.smooth_f, &d.smooth_f) && upload(h.smooth_t, &d.smooth_t);
     if (!ok) {
         set_error(std::string("table upload failed: ") + cudaGetErrorString(cudaGetLastError()));

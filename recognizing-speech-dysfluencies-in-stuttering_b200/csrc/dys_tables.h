@@ -26,6 +26,7 @@ constexpr int kPipLo = 20;              // 150 Hz <= k * 7.8125 < 4000 Hz  ->  k
 constexpr int kPipHi = 511;
 constexpr int kMaxPeaksPerFrame = 246;  // strict-left / weak-right local maxima cannot be adjacent
 // spectral gate (noisereduce defaults inherited by pipeline1.py:140)
+constexpr int kChromaPitch = 1032;      // bins per plane of the device chroma table (float4 units)
 constexpr int kNrFft = 1024;
 constexpr int kNrHop = 256;
 constexpr int kNrBins = 513;
@@ -48,10 +49,12 @@ struct HostTables {
     std::vector<float> mel_dense;           // [128*1025] (debug / tests only, host side)
     std::vector<float> dct;                 // [20*128]  ortho DCT-II rows
     std::vector<float> chroma;              // [100][1025][12]
+    // device layout of the same weights: three planes of 4 chroma rows each, [100][3][kChromaPitch] float4, so the 32
+    // lanes of a warp (one bin each) read 512 contiguous bytes per plane (the bin-major rows are 48 B apart)
+    std::vector<float> chroma_planes;
     std::vector<double> tuning_edges;       // [101]
     std::vector<double> hann1024;           // [1024]
     std::vector<double2> tw512;             // [16*32]
-    std::vector<double2> tw32h;             // [2*16]
     std::vector<double2> split1024;         // [512]
     std::vector<double> wss;                // [256]  istft window-sum-square, interior
     std::vector<double> smooth_f, smooth_t; // [33], [7]
@@ -70,11 +73,10 @@ struct DeviceTables {
     int mel_goff[4];
     int mel_wt_len;
     const float* dct;
-    const float* chroma;
+    const float4* chroma;                   // plane-major (HostTables::chroma_planes)
     const double* tuning_edges;
     const double* hann1024;
     const double2* tw512;
-    const double2* tw32h;
     const double2* split1024;
     const double* wss;
     const double* smooth_f;
