@@ -113,7 +113,9 @@ DYS_API int dys_qc_metrics(const float* d_audio, const int64_t* d_starts, const 
 /* Copies a host-side table: which = 0 mel filterbank float32[128*1025], 1 DCT float32[20*128],
  * 2 chroma filterbank of tuning index `arg` float32[1025*12] ([bin][chroma]), 3 hann2048 float32[2048],
  * 4 tuning edges float64[101], 5 smoothing taps float64[33+7], 6 istft window-sum-square float64[256],
- * 7 iir b float64[1].  Returns the element count, or -1. */
+ * 7 iir b float64[1], 8 lane-per-filter mel runs int32[128 starts + 128 lengths + 4 group offsets] (padded in front so
+ * that the 32 starts of a group differ mod 32), 9 their step-major weights float32[32*88] (filter f = lane + 32 g, step j
+ * at offset[g] + 32 j + lane).  Returns the element count, or -1. */
 DYS_API int64_t dys_get_table(int32_t which, int32_t arg, void* h_out, int64_t max_elems);
 
 /* Runs the feature path for ONE clip already on the device and exposes the intermediates:

@@ -244,6 +244,8 @@ DYS_API int64_t dys_get_table(int32_t which, int32_t arg, void* h_out, int64_t m
     int64_t n = 0;
     size_t esz = 4;
     double taps[kNrFreqTaps + kNrTimeTaps];
+    int32_t runs[2 * kMels + 4];
+    float wt[kMelWtMax];
     switch (which) {
         case 0: src = h.mel_dense.data(); n = int64_t(h.mel_dense.size()); break;
         case 1: src = h.dct.data(); n = int64_t(h.dct.size()); break;
@@ -258,6 +260,15 @@ DYS_API int64_t dys_get_table(int32_t which, int32_t arg, void* h_out, int64_t m
             src = taps; n = kNrFreqTaps + kNrTimeTaps; esz = 8; break;
         case 6: src = h.wss.data(); n = kNrHop; esz = 8; break;
         case 7: src = &h.iir_b; n = 1; esz = 8; break;
+        case 8:
+            std::copy(h.mel_rstart.begin(), h.mel_rstart.end(), runs);
+            std::copy(h.mel_rlen.begin(), h.mel_rlen.end(), runs + kMels);
+            std::copy(h.mel_goff, h.mel_goff + 4, runs + 2 * kMels);
+            src = runs; n = 2 * kMels + 4; break;
+        case 9:
+            std::fill(wt, wt + kMelWtMax, 0.f);
+            std::copy(h.mel_wt.begin(), h.mel_wt.begin() + std::min<size_t>(h.mel_wt.size(), kMelWtMax), wt);
+            src = wt; n = kMelWtMax; break;
         default: return -1;
     }
     if (!h_out || max_elems < n) return -1;

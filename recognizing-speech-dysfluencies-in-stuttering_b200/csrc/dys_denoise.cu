@@ -402,11 +402,16 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
     bool bad = false;
     int cbuf = 0;
 
+    auto frame_ok = [&](int t) { return t >= g.t_first && t <= g.t_last && t <= he + 1; };
     // block h is the sum of frames h-1 .. h+2: frames hb-1 .. he+1 are needed
     for (int T0 = hb - 1; T0 - 2 < he; T0 += W) {
         const int t = T0 + warp;
-        if (t >= g.t_first && t <= g.t_last && t <= he + 1) {
+        if (frame_ok(t)) {
             const double* trow = tsm + size_t(t - g.t_first) * kNrBinsPad;
+            double2 mr[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mr[j] = __ldg(reinterpret_cast<const double2*>(trow + 2 * lane + 64 * j));
+            const double mr512 = lane == 0 ? __ldg(trow + 512) : 0.0;
             const double2* srow = spec + size_t(t - g.t_first) * kNrBinsPad;
             const LaneTrig tr = per_frame(trig);
             if (t + W <= g.t_last && t + W <= he + 1) {         // this warp's next frame: pull both rows towards L2
@@ -431,15 +436,10 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
             const double gain = prop * (1.0 / 289.0);
             {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int k = 2 * lane + 64 * j;
-                    const double2 v = __ldg(reinterpret_cast<const double2*>(trow + k));
-                    *reinterpret_cast<double2*>(rb + seg_idx(k)) = v;
-                }
+                for (int j = 0; j < 8; ++j) *reinterpret_cast<double2*>(rb + seg_idx(2 * lane + 64 * j)) = mr[j];
                 if (lane < 12) {                                // bins 512 .. 527 (only 512 is data) and the zero halo -8 .. -1
                     const int k = lane < 8 ? 512 + 2 * lane : 2 * (lane - 8) - 8;
-                    const double v0 = lane == 0 ? __ldg(trow + 512) : 0.0;
-                    *reinterpret_cast<double2*>(rb + seg_idx(k)) = make_double2(v0, 0.0);
+                    *reinterpret_cast<double2*>(rb + seg_idx(k)) = make_double2(lane == 0 ? mr512 : 0.0, 0.0);
                 }
             }
             __syncwarp();

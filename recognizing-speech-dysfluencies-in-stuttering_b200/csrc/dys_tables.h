@@ -40,7 +40,8 @@ struct HostTables {
     std::vector<float> hann2048;            // [2048]
     std::vector<float2> tw1024;             // [32*32]  W_1024^(l*kA) at kA*32+l  (x = cos, y = -sin)
     std::vector<float2> split2048;          // [1024]   (cos, sin)(2 pi k / 2048)
-    std::vector<int> mel_start, mel_len, mel_ptr;   // [128]
+    std::vector<int> mel_start, mel_len, mel_ptr;   // [128]  support of every filter
+    std::vector<int> mel_rstart, mel_rlen;          // [128]  the same, padded in front so that a group's 32 starts differ mod 32
     std::vector<float> mel_w;               // [2020]
     // the same weights step-major for the lane-per-filter loop: filter f = lane + 32 g, its j-th bin at
     // mel_wt[mel_goff[g] + 32 j + lane] -> the 32 simultaneous weight reads are conflict-free
@@ -65,7 +66,7 @@ struct DeviceTables {
     const float* hann2048;
     const float2* tw1024;
     const float2* split2048;
-    const int* mel_start;
+    const int* mel_start;                   // HostTables::mel_rstart / mel_rlen (padded runs)
     const int* mel_len;
     const int* mel_ptr;
     const float* mel_w;

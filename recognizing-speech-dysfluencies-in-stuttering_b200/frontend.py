@@ -767,7 +767,7 @@ def get_table(which: int, arg: int = 0) -> np.ndarray:
     lib = _lib.load()
     shapes = {0: ((128, 1025), np.float32), 1: ((20, 128), np.float32), 2: ((1025, 12), np.float32),
               3: ((2048,), np.float32), 4: ((101,), np.float64), 5: ((40,), np.float64), 6: ((256,), np.float64),
-              7: ((1,), np.float64)}
+              7: ((1,), np.float64), 8: ((260,), np.int32), 9: ((32 * 88,), np.float32)}
     shape, dt = shapes[which]
     out = np.empty(shape, dtype=dt)
     got = lib.dys_get_table(which, arg, out.ctypes.data, out.size)

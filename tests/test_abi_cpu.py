@@ -54,6 +54,27 @@ def test_tables_match_oracle(pkg):
     assert fe.get_table(7)[0] == denoise.iir_coefficient()
 
 
+def test_mel_runs_are_conflict_free_and_exact(pkg):
+    """The lane-per-filter layout of the sparse mel bank: every group's 32 run starts differ mod 32 (no shared-memory bank
+    conflicts on the power reads), the leading padding is zero weights only, no step was added, and the runs reproduce
+    librosa's filterbank exactly."""
+    fe = pkg.frontend
+    runs, wt, dense = fe.get_table(8), fe.get_table(9), fe.get_table(0)
+    start, length, goff = runs[:128], runs[128:256], runs[256:]
+    rebuilt = np.zeros_like(dense)
+    steps = 0
+    for g in range(4):
+        s, l = start[32 * g:32 * g + 32], length[32 * g:32 * g + 32]
+        assert len(set(int(v) % 32 for v in s)) == 32
+        assert s.min() >= 0 and (s + l).max() <= 1025
+        steps += int(l.max())
+        for lane in range(32):
+            for j in range(int(l[lane])):
+                rebuilt[32 * g + lane, s[lane] + j] = wt[goff[g] + 32 * j + lane]
+    assert np.array_equal(rebuilt, dense)
+    assert steps == 86
+
+
 def test_no_cpu_fallback(pkg):
     import torch
     if torch.cuda.is_available():
