@@ -33,6 +33,11 @@ namespace dys {
 
 namespace {
 
+// spectrum bins (x 32 lanes) whose loads are issued before the second running sum of the mask smoothing
+#ifndef DYS_APPLY_XEARLY
+#define DYS_APPLY_XEARLY 8
+#endif
+
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr int kFramesPerCta = 64;
@@ -480,6 +485,13 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
                 }
             }
             __syncwarp();
+            double2 x[16];
+#if DYS_APPLY_XEARLY
+            static_for<DYS_APPLY_XEARLY>([&](auto iq) {          // part of the spectrum row in flight during the second running sum
+                constexpr int q = decltype(iq)::value;
+                x[q] = __ldg(srow + lane + 32 * q);
+            });
+#endif
             {
                 double B[33];                                   // B[i] = B1[16 L - 8 + i]
                 static_for<4>([&](auto ic) {
@@ -508,9 +520,8 @@ k_nr_apply_ola(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrS
                 }
             }
             __syncwarp();
-            double2 x[16];
-            static_for<16>([&](auto iq) {
-                constexpr int q = decltype(iq)::value;
+            static_for<16 - DYS_APPLY_XEARLY>([&](auto iq) {
+                constexpr int q = decltype(iq)::value + DYS_APPLY_XEARLY;
                 x[q] = __ldg(srow + lane + 32 * q);
             });
             double nyq = __ldg(&srow[512].x);
