@@ -35,7 +35,7 @@ namespace {
 
 // spectrum bins (x 32 lanes) whose loads are issued before the second running sum of the mask smoothing
 #ifndef DYS_APPLY_XEARLY
-#define DYS_APPLY_XEARLY 8
+#define DYS_APPLY_XEARLY 12
 #endif
 
 constexpr int kWarps = 8;
