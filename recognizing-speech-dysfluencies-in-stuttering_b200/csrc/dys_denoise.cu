@@ -223,7 +223,12 @@ k_nr_stft_mag(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
 // ------------------------------------------------------------------------------------------
 // filtfilt([b], [1, b - 1]) over time + sigmoid + 7-tap time smoothing, one thread per bin.
 constexpr int kIirThreads = 32;
+#ifndef DYS_IIR_FWD
+#define DYS_IIR_FWD 8
+#endif
+constexpr int kIirFwd = DYS_IIR_FWD;                // rows per batch of the forward sweep (divides the check-point spacing)
 constexpr int kIirCkShift = 7;                       // forward state check-pointed every 128 frames
+static_assert((1 << kIirCkShift) % kIirFwd == 0, "check-point rows must fall on batch ends of the forward sweep");
 constexpr int kIirMaxCk = 24;                        // covers ta_max <= 3072 (a full 660 000-sample chunk has 2579)
 
 __global__ void __launch_bounds__(kIirThreads)
@@ -240,30 +245,26 @@ k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
     // forward: f[t] = b A[t] + (1 - b) f[t-1],  f[-1] := A[0]  (lfilter_zi steady state; A[0] = 0 when padded)
     double prev = (g.t_first == 0) ? col[0] : 0.0;
     int i = 0;
-    {   // batches of 8 rows, the next batch's loads in flight while the serial recurrence runs over the current one
-        double a[8], an[8];
-        if (Ta >= 8) {
+    {   // The sweep has two flops per row and waits on DRAM: batches of kIirFwd rows, the next batch's loads in flight while
+        // the serial recurrence runs over the current one, and the ragged tail fetched as one more (predicated) batch
+        // instead of row by row.  (The registers are free here: the backward sweep below needs more.)
+        double a[kIirFwd], an[kIirFwd];
+        auto load_batch = [&](double (&d)[kIirFwd], int i0) {
 #pragma unroll
-            for (int u = 0; u < 8; ++u) a[u] = col[size_t(u) * P];
+            for (int u = 0; u < kIirFwd; ++u) d[u] = (i0 + u < Ta) ? col[size_t(i0 + u) * P] : 0.0;
+        };
+        load_batch(a, 0);
+        for (; i + kIirFwd <= Ta; i += kIirFwd) {
+            load_batch(an, i + kIirFwd);
+#pragma unroll
+            for (int u = 0; u < kIirFwd; ++u) prev = b * a[u] + r * prev;
+            if (((i + kIirFwd) & ((1 << kIirCkShift) - 1)) == 0) ck[((i + kIirFwd) >> kIirCkShift) - 1][threadIdx.x] = prev;
+#pragma unroll
+            for (int u = 0; u < kIirFwd; ++u) a[u] = an[u];
         }
-        for (; i + 8 <= Ta; i += 8) {
-            const bool more = i + 16 <= Ta;
-            if (more) {
 #pragma unroll
-                for (int u = 0; u < 8; ++u) an[u] = col[size_t(i + 8 + u) * P];
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) prev = b * a[u] + r * prev;
-            if (((i + 8) & ((1 << kIirCkShift) - 1)) == 0) ck[((i + 8) >> kIirCkShift) - 1][threadIdx.x] = prev;
-            if (more) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) a[u] = an[u];
-            }
-        }
-    }
-    for (; i < Ta; ++i) {
-        prev = b * col[size_t(i) * P] + r * prev;
-        if (((i + 1) & ((1 << kIirCkShift) - 1)) == 0) ck[i >> kIirCkShift][threadIdx.x] = prev;
+        for (int u = 0; u < kIirFwd; ++u)                   // fewer than kIirFwd rows left: none of them is a check-point row
+            if (i + u < Ta) prev = b * a[u] + r * prev;
     }
     // frames t_last+1 .. Tn-1 hold zeros: f decays geometrically and the backward recursion over them,
     // started from S[Tn] := f[Tn-1], collapses to  S[t_last+1] = r F u,  u <- b + r^2 u  (m-1 times from 1).
