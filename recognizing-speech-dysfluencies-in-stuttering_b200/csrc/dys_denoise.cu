@@ -40,7 +40,12 @@ namespace {
 
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
-constexpr int kFramesPerCta = 64;
+// Launch groups with at least this many chunks fill the machine twice over with ONE CTA per chunk: k_nr_stft_mag then
+// gives a CTA 192 frames instead of 64 (its 24 KB of tables are loaded once per CTA: -2 %) and k_nr_apply_ola 24 rounds
+// instead of 8 (no frames transformed twice at CTA seams: -1.6 %).  Smaller groups keep the short CTAs: a single clip's
+// latency is set by how many SMs its frames spread over.
+constexpr int kBigGroup = 592;
+constexpr int kFramesPerCtaSmall = 64, kFramesPerCtaBig = 192;
 
 struct NrGeom {
     int clip, n, c0, out_len, L, Tn, t_first, t_last;
@@ -184,15 +189,15 @@ struct MagSmem {
 };
 
 __global__ void __launch_bounds__(kThreads, 2)
-k_nr_stft_mag(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrScratch sc) {
+k_nr_stft_mag(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrScratch sc, int frames_per_cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MagSmem& sm = *reinterpret_cast<MagSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int li = blockIdx.x;
     const NrGeom g = nr_geom(cv, item0 + li, cpc);
-    const int t_begin = g.t_first + blockIdx.y * kFramesPerCta;
+    const int t_begin = g.t_first + blockIdx.y * frames_per_cta;
     if (t_begin > g.t_last) return;
-    const int t_end = min(g.t_last + 1, t_begin + kFramesPerCta);
+    const int t_end = min(g.t_last + 1, t_begin + frames_per_cta);
     nr_load_tables(sm.tab, tb, tid, kThreads);
     nr_load_fwd_tables(sm.fwd, tb, tid, kThreads);
     __syncthreads();
@@ -701,22 +706,24 @@ cudaError_t launch_denoise(const DeviceTables& tb, const ClipView& cv, float* cl
     if (cudaError_t e = ensure_dynamic_smem<kK_nr_stft_mag>(k_nr_stft_mag, int(sizeof(MagSmem)))) return e;
     if (cudaError_t e = ensure_dynamic_smem<kK_nr_apply_ola>(k_nr_apply_ola<kApplyWarps>, int(sizeof(ApplySmem<kApplyWarps>)))) return e;
     if (sc.ta_max > kIirMaxCk << kIirCkShift) return cudaErrorInvalidValue;
-    const int gy = (sc.ta_max + kFramesPerCta - 1) / kFramesPerCta;
+    const bool big = n_items >= kBigGroup;
+    const int fpc = big ? kFramesPerCtaBig : kFramesPerCtaSmall;
+    const int gy = (sc.ta_max + fpc - 1) / fpc;
     ClipView cvw = cv;
     cvw.clean = clean; cvw.clean_peak = clean_peak; cvw.clean_flag = clean_flag;
     { LaunchScope ls(kK_nr_stft_mag, stream);
-      k_nr_stft_mag<<<dim3(n_items, gy), kThreads, sizeof(MagSmem), stream>>>(tb, cvw, cpc, item0, sc); }
+      k_nr_stft_mag<<<dim3(n_items, gy), kThreads, sizeof(MagSmem), stream>>>(tb, cvw, cpc, item0, sc, fpc); }
     { LaunchScope ls(kK_nr_iir_mask, stream);
       k_nr_iir_mask<<<dim3(n_items, (kNrBins + kIirThreads - 1) / kIirThreads), kIirThreads, 0, stream>>>(tb, cvw, cpc, item0, sc,
                                                                                                       clean_flag); }
     // output blocks of 256 samples per chunk, split evenly over CTAs of about 16 W frames
     const int max_out = std::min(cv.max_len, kNrChunk);
     const int n_blocks = (kNrPad + std::max(max_out, 1) - 1) / kNrHop - kNrPad / kNrHop + 1;
-    // A CTA that owns b blocks transforms b + 3 frames in rounds of kApplyWarps: pick the rounds per CTA (4..12) that
-    // leave the fewest idle warp slots over the whole chunk (a 3-s clip: 188 blocks -> 61 + 61 + 61 + 5 = 25 rounds;
-    // the even split 4 x 47 ran 28).
+    // A CTA that owns b blocks transforms b + 3 frames in rounds of kApplyWarps: pick the rounds per CTA that leave the
+    // fewest idle warp slots over the whole chunk (a 3-s clip: 188 blocks -> 61 + 61 + 61 + 5 = 25 rounds, or one CTA of
+    // 24 rounds in a big launch group; the even split 4 x 47 ran 28).
     int blocks_per_cta = kApplyWarps * 8 - 3, best_rounds = INT_MAX;
-    for (int r : {8, 7, 9, 6, 10, 5, 11, 12, 4}) {
+    for (int r : {big ? 24 : 8, 8, 7, 9, 6, 10, 5, 11, 12, 4}) {
         const int bpc = kApplyWarps * r - 3;
         const int full = (n_blocks - 1) / bpc, last = n_blocks - full * bpc;
         const int rounds = full * r + (last + 3 + kApplyWarps - 1) / kApplyWarps;

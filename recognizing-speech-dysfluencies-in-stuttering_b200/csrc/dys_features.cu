@@ -30,7 +30,7 @@ namespace {
 
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
-constexpr int kFramesPerCta = 96;            // 12 frames per warp; one CTA covers a 3-s clip (94 frames)
+constexpr int kFramesPerCta = 96;            // 12 frames per warp; one CTA covers a 3-s clip (94 frames; two CTAs of 48: +5 %)
 
 __device__ __forceinline__ int enc_f32(float f) {
     int i = __float_as_int(f);
