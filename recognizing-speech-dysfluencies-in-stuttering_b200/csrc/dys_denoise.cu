@@ -9,16 +9,18 @@
 // float64; so do these kernels, because the PCM-16 quantiser that follows (pipeline1.py:142)
 // turns float32-level errors into LSB flips.
 //
-//   k_nr_stft_mag  : one warp per frame, 512-point complex fp64 FFT  -> |D|            [frames x 513]
+//   k_nr_stft_mag  : one warp per frame, 512-point complex fp64 FFT + real split -> complex spectrum D and |D|
+//                    [frames x 513 each]
 //   k_nr_iir_mask  : one thread per (chunk, bin), sequential in time: forward IIR (only check-points
 //                    kept), closed-form zero tail, backward IIR with the forward state re-derived in
 //                    reverse, sigmoid, and the 7-tap time smoothing of the mask through a register
-//                    window -> time-smoothed mask, in place.  NaN (0/0) raises the clip's fallback flag
-//   k_nr_apply_ola : one warp per frame: FFT again, 33-tap frequency smoothing of the mask row
-//                    (register-tiled, taps in constant memory), * mask, inverse FFT, synthesis window;
-//                    the CTA overlap-adds its frames in shared memory (ascending frame order, like
-//                    librosa's __overlap_add), divides by the window-sum-square, stores float32 and
-//                    maxes the clip peak.  Inverse frames never touch HBM.
+//                    window -> time-smoothed mask, in place of |D|.  NaN (0/0) raises the clip's fallback flag
+//   k_nr_apply_ola : one warp per frame: 33-tap frequency smoothing of the mask row (two cascaded 17-bin
+//                    running sums in registers, 16 bins per lane, halos through the warp's shared-memory
+//                    tile), stored spectrum * mask, inverse FFT, synthesis window; the CTA overlap-adds its
+//                    frames in shared memory (ascending frame order, like librosa's __overlap_add),
+//                    scales by 1 / window-sum-square, stores float32 and maxes the clip peak.  Inverse
+//                    frames never touch HBM.
 // Only frames that overlap the un-padded samples are touched (191 of 422 for a 3-s clip).
 #include <algorithm>
 #include <cfloat>
