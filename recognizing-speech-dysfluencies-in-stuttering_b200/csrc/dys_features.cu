@@ -13,7 +13,7 @@
 //                     registers -- reduced to 128 log-mel values and to the piptrack peak list.
 //   k_tuning        : one CTA per clip: exact median (radix select) of the peak magnitudes,
 //                     100-bin residual histogram, first arg-max  -> tuning index.
-//   k_frame_cepstra : one warp per 4 frames (every chroma weight load feeds 4 x 12 FMAs): top-dB clamp +
+//   k_frame_cepstra : one warp per 6 frames (every chroma weight load feeds 6 x 12 FMAs): top-dB clamp +
 //                     DCT-II (20x128) and the 12x1025 chroma projection with the tuning's filterbank + inf-norm.
 //   k_clip_stats    : one CTA per clip: delta / delta-delta (Savitzky-Golay taps, replicated
 //                     edges) and mean / population std of every row -> the 149-vector.
