@@ -52,10 +52,13 @@ def _tri(n: int) -> np.ndarray:
 
 
 @functools.lru_cache(maxsize=None)
-def smoothing_filter() -> np.ndarray:
-    """noisereduce _smoothing_filter(n_grad_freq=16, n_grad_time=3): [33, 7], sums to 1."""
-    n_grad_freq = int(500 / (SR / (NR_N_FFT / 2)))
-    n_grad_time = int(50 / ((NR_HOP / SR) * 1000))
+def smoothing_filter(n_grad_freq: int | None = None, n_grad_time: int | None = None) -> np.ndarray:
+    """noisereduce _smoothing_filter(n_grad_freq=16, n_grad_time=3): [33, 7], sums to 1.
+    (The arguments exist for the discrimination test only: tests perturb them and must FAIL against the goldens.)"""
+    if n_grad_freq is None:
+        n_grad_freq = int(500 / (SR / (NR_N_FFT / 2)))
+    if n_grad_time is None:
+        n_grad_time = int(50 / ((NR_HOP / SR) * 1000))
     f = np.outer(_tri(n_grad_freq), _tri(n_grad_time))
     return f / np.sum(f)
 
@@ -94,16 +97,21 @@ def nr_istft(D: np.ndarray) -> np.ndarray:
     return y
 
 
-def spectral_gate_chunk(chunk: np.ndarray, prop_decrease: float = 1.0, return_parts: bool = False):
-    """SpectralGateNonStationary.spectral_gating_nonstationary on one padded float64 chunk."""
+def spectral_gate_chunk(chunk: np.ndarray, prop_decrease: float = 1.0, return_parts: bool = False, perturb: dict | None = None):
+    """SpectralGateNonStationary.spectral_gating_nonstationary on one padded float64 chunk.
+    ``perturb`` (tests only) overrides thresh / slope / n_grad_freq / n_grad_time / time_constant_s."""
+    pt = perturb or {}
     D = nr_stft(chunk)
     A = np.abs(D)
     b = iir_coefficient()
+    if "time_constant_s" in pt:
+        t_frames = pt["time_constant_s"] * SR / float(NR_HOP)
+        b = float((np.sqrt(1 + 4 * t_frames ** 2) - 1) / (2 * t_frames ** 2))
     S = scipy.signal.filtfilt([b], [1, b - 1], A, axis=-1, padtype=None)
     with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
         above = (A - S) / S
-        mask0 = 1 / (1 + np.exp(-(above + -NR_THRESH) * NR_SLOPE))
-    mask = scipy.signal.fftconvolve(mask0, smoothing_filter(), mode="same")
+        mask0 = 1 / (1 + np.exp(-(above + -pt.get("thresh", NR_THRESH)) * pt.get("slope", NR_SLOPE)))
+    mask = scipy.signal.fftconvolve(mask0, smoothing_filter(pt.get("n_grad_freq"), pt.get("n_grad_time")), mode="same")
     mask = mask * prop_decrease + np.ones(np.shape(mask)) * (1.0 - prop_decrease)
     y = nr_istft(D * mask)
     out = np.zeros(chunk.shape, chunk.dtype)
@@ -113,7 +121,7 @@ def spectral_gate_chunk(chunk: np.ndarray, prop_decrease: float = 1.0, return_pa
     return out
 
 
-def reduce_noise(y: np.ndarray, prop_decrease: float = 1.0) -> np.ndarray:
+def reduce_noise(y: np.ndarray, prop_decrease: float = 1.0, perturb: dict | None = None) -> np.ndarray:
     """nr.reduce_noise(y=y, sr=16000) for a 1-D float32 clip -> float32, same length.
     Inputs longer than 600 000 samples are gated in 600 000-sample chunks, each padded
     with 30 000 neighbouring samples (zeros outside the clip) -- SpectralGate.get_traces."""
@@ -126,7 +134,7 @@ def reduce_noise(y: np.ndarray, prop_decrease: float = 1.0) -> np.ndarray:
         chunk = np.zeros(i2 - i1, dtype=np.float64)
         if bnd > a:
             chunk[a - i1:bnd - i1] = y[a:bnd]
-        return spectral_gate_chunk(chunk, prop_decrease)[start - i1:end - i1]
+        return spectral_gate_chunk(chunk, prop_decrease, perturb=perturb)[start - i1:end - i1]
 
     if n > NR_CHUNK:
         out = np.zeros(n, dtype=y.dtype)
@@ -151,7 +159,7 @@ def peak_normalize(y: np.ndarray) -> np.ndarray:
     return out
 
 
-def clean_audio(y: np.ndarray, prop_decrease: float = 1.0):
+def clean_audio(y: np.ndarray, prop_decrease: float = 1.0, perturb: dict | None = None):
     """In-memory clean_audio_and_cache (pipeline1.py:136-143): returns the int16 PCM that
     the reference writes to clear_audio/<stem>.wav, or ``None`` where the reference's
     ``except`` branch fires (pipeline1.py:144-146), e.g. the all-zero clip (0/0 -> NaN)."""
@@ -161,7 +169,7 @@ def clean_audio(y: np.ndarray, prop_decrease: float = 1.0):
     try:
         if y.size == 0:
             raise ValueError("empty")
-        return quantize_pcm16(peak_normalize(reduce_noise(y, prop_decrease)))
+        return quantize_pcm16(peak_normalize(reduce_noise(y, prop_decrease, perturb)))
     except Exception:
         return None
 
