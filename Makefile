@@ -4,7 +4,7 @@ CSRC     := $(PKG)/csrc
 NVCC     ?= /usr/local/cuda/bin/nvcc
 ARCH     := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS  := -O3 -std=c++17 -lineinfo $(ARCH) -Xcompiler -fPIC -Xcompiler -fvisibility=hidden --expt-relaxed-constexpr $(VARIANT_FLAGS)
-SRCS     := $(CSRC)/dys_api.cu $(CSRC)/dys_tables.cu $(CSRC)/dys_features.cu $(CSRC)/dys_denoise.cu $(CSRC)/dys_cmvn.cu $(CSRC)/dys_qc.cu $(CSRC)/dys_profile.cu
+SRCS     := $(CSRC)/dys_api.cu $(CSRC)/dys_tables.cu $(CSRC)/dys_features.cu $(CSRC)/dys_denoise.cu $(CSRC)/dys_cmvn.cu $(CSRC)/dys_qc.cu $(CSRC)/dys_profile.cu $(CSRC)/dys_resample.cu
 OBJS     := $(SRCS:.cu=.o)
 LIB      ?= $(PKG)/libdysb200.so
 

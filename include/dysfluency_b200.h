@@ -88,6 +88,33 @@ DYS_API int dys_features_raw_clean(const float* d_audio, const int64_t* d_starts
                            int32_t* d_status, int16_t* d_clean_pcm, const int64_t* d_pcm_starts, void* d_workspace,
                            int64_t workspace_bytes, void* stream);
 
+/* The same two entry points for 16-bit PCM input: sample value = d_pcm[i] / 32768, exactly what
+ * librosa.load returns for a PCM-16 WAV (the reference's clean branch and its clear_audio/ corpus,
+ * pipeline1.py:389, 437).  Results are bit-identical to the float32 entry points fed int16 / 32768.0f;
+ * half the bytes cross PCIe and HBM.  Even d_starts keep the 4-byte vector loads. */
+DYS_API int dys_features_raw_pcm16(const int16_t* d_pcm, const int64_t* d_starts, const int32_t* d_lengths, int32_t n_clips,
+                                   int32_t max_len, float* d_out, int32_t* d_status, void* d_workspace, int64_t workspace_bytes,
+                                   void* stream);
+DYS_API int dys_features_raw_clean_pcm16(const int16_t* d_pcm, const int64_t* d_starts, const int32_t* d_lengths, int32_t n_clips,
+                                         int32_t max_len, float prop_decrease, float* d_out_raw, float* d_out_clean,
+                                         int32_t* d_status, int16_t* d_clean_pcm, const int64_t* d_pcm_starts, void* d_workspace,
+                                         int64_t workspace_bytes, void* stream);
+
+/* Rate conversion to 16 kHz: the resampling half of librosa.load(path, sr=16000)            [pipeline1.py:102]
+ * (soxr "HQ": linear phase, pass-band to 0.9136 x the lower Nyquist, stop-band from it, 126 dB; restated from soxr's
+ * published recipe -- parity with the reference's *_raw_feats.npy is statistical).
+ *   d_in        float32 samples, or int16 PCM when in_is_pcm16 != 0 (value = q / 32768)
+ *   clip c      d_in[d_in_starts[c] .. + d_in_lengths[c])  ->  d_out[d_out_starts[c] .. + dys_resampled_length(len, sr_in))
+ *   sr_in       any rate whose ratio to 16000 reduces to at most 4096 / 8192 (22050, 44100, 48000, 32000, 24000, 11025, 8000, ...)
+ */
+DYS_API int64_t dys_resampled_length(int64_t n_in, int32_t sr_in);
+DYS_API int dys_resample_to_16k(const void* d_in, int32_t in_is_pcm16, int32_t sr_in, const int64_t* d_in_starts,
+                                const int32_t* d_in_lengths, int32_t n_clips, int32_t max_in_len, float* d_out,
+                                const int64_t* d_out_starts, void* stream);
+/* Host copy of the polyphase table h[up][ntaps] (float64) for the parity tests; h_meta = {up, down, half, ntaps}.
+ * Returns up * ntaps, 0 for an unsupported rate, -1 when max_elems is too small.  h_out may be NULL. */
+DYS_API int64_t dys_resample_table(int32_t sr_in, double* h_out, int64_t max_elems, int32_t* h_meta);
+
 /* StandardScaler().fit building block                            [pipeline1.py:470-471]
  *   d_acc (float64[299]) <- [n_rows, sum_f (x - shift), sum_f (x - shift)^2]; d_shift NULL = 0.
  *   Per-GPU accumulators add across ranks (one NCCL all-reduce of 299 doubles).

@@ -29,6 +29,11 @@ _SIGNATURES = {
     "dys_workspace_min_bytes": (_i64, [_i32, _i32, _i32]),
     "dys_features_raw": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
     "dys_features_raw_clean": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "dys_features_raw_pcm16": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),
+    "dys_features_raw_clean_pcm16": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "dys_resampled_length": (_i64, [_i64, _i32]),
+    "dys_resample_to_16k": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "dys_resample_table": (_i64, [_i32, _vp, _i64, _vp]),
     "dys_cmvn_accumulate": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),
     "dys_cmvn_finalize": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "dys_cmvn_apply": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp]),

@@ -62,6 +62,14 @@ Layout make_layout(int n_clips, int max_len, bool with_clean) {
     return L;
 }
 
+int check_common(const void* d_audio, const void* d_starts, const void* d_lengths, int n_clips, int max_len);
+int features_raw_impl(const float* d_audio, const int16_t* d_pcm, const int64_t* d_starts, const int32_t* d_lengths, int32_t n_clips,
+                      int32_t max_len, float* d_out, int32_t* d_status, void* d_workspace, int64_t workspace_bytes, void* stream);
+int features_raw_clean_impl(const float* d_audio, const int16_t* d_pcm, const int64_t* d_starts, const int32_t* d_lengths,
+                            int32_t n_clips, int32_t max_len, float prop_decrease, float* d_out_raw, float* d_out_clean,
+                            int32_t* d_status, int16_t* d_clean_pcm, const int64_t* d_pcm_starts, void* d_workspace,
+                            int64_t workspace_bytes, void* stream);
+
 int check_common(const void* d_audio, const void* d_starts, const void* d_lengths, int n_clips, int max_len) {
     if (n_clips < 0 || max_len < 0) { set_error("n_clips and max_len must be >= 0"); return DYS_ERR_INVALID; }
     if (n_clips > 0 && (!d_audio || !d_starts || !d_lengths)) { set_error("null device pointer"); return DYS_ERR_INVALID; }
@@ -92,7 +100,7 @@ using namespace dys;
 
 extern "C" {
 
-DYS_API int dys_version(void) { return 100; }
+DYS_API int dys_version(void) { return 200; }
 
 DYS_API const char* dys_last_error(void) { return last_error_cstr(); }
 
@@ -128,7 +136,57 @@ DYS_API int64_t dys_workspace_min_bytes(int32_t n_clips, int32_t max_len, int32_
 DYS_API int dys_features_raw(const float* d_audio, const int64_t* d_starts, const int32_t* d_lengths, int32_t n_clips,
                      int32_t max_len, float* d_out, int32_t* d_status, void* d_workspace, int64_t workspace_bytes,
                      void* stream) {
-    if (int rc = check_common(d_audio, d_starts, d_lengths, n_clips, max_len)) return rc;
+    return features_raw_impl(d_audio, nullptr, d_starts, d_lengths, n_clips, max_len, d_out, d_status, d_workspace,
+                             workspace_bytes, stream);
+}
+
+DYS_API int dys_features_raw_pcm16(const int16_t* d_pcm, const int64_t* d_starts, const int32_t* d_lengths, int32_t n_clips,
+                                   int32_t max_len, float* d_out, int32_t* d_status, void* d_workspace, int64_t workspace_bytes,
+                                   void* stream) {
+    return features_raw_impl(nullptr, d_pcm, d_starts, d_lengths, n_clips, max_len, d_out, d_status, d_workspace,
+                             workspace_bytes, stream);
+}
+
+DYS_API int dys_features_raw_clean_pcm16(const int16_t* d_pcm, const int64_t* d_starts, const int32_t* d_lengths, int32_t n_clips,
+                                         int32_t max_len, float prop_decrease, float* d_out_raw, float* d_out_clean,
+                                         int32_t* d_status, int16_t* d_clean_pcm, const int64_t* d_pcm_starts, void* d_workspace,
+                                         int64_t workspace_bytes, void* stream) {
+    return features_raw_clean_impl(nullptr, d_pcm, d_starts, d_lengths, n_clips, max_len, prop_decrease, d_out_raw, d_out_clean,
+                                   d_status, d_clean_pcm, d_pcm_starts, d_workspace, workspace_bytes, stream);
+}
+
+DYS_API int64_t dys_resampled_length(int64_t n_in, int32_t sr_in) {
+    if (n_in < 0 || sr_in <= 0) return -1;
+    if (sr_in == kSR) return n_in;
+    return (n_in * kSR + sr_in - 1) / sr_in;                 // librosa.resample: ceil(n * target_sr / orig_sr)
+}
+
+DYS_API int dys_resample_to_16k(const void* d_in, int32_t in_is_pcm16, int32_t sr_in, const int64_t* d_in_starts,
+                                const int32_t* d_in_lengths, int32_t n_clips, int32_t max_in_len, float* d_out,
+                                const int64_t* d_out_starts, void* stream) {
+    if (n_clips < 0 || max_in_len < 0) { set_error("n_clips and max_in_len must be >= 0"); return DYS_ERR_INVALID; }
+    if (n_clips == 0) return DYS_OK;
+    if (!d_in || !d_in_starts || !d_in_lengths || !d_out || !d_out_starts) { set_error("null device pointer"); return DYS_ERR_INVALID; }
+    if (sr_in == kSR) { set_error("sr_in is already 16000: nothing to resample"); return DYS_ERR_INVALID; }
+    if (resample_table_host(sr_in, nullptr, 0, nullptr) <= 0) { set_error("unsupported input sample rate"); return DYS_ERR_INVALID; }
+    if (!device_tables()) return DYS_ERR_CUDA;
+    DYS_CUDA_OK(launch_resample(in_is_pcm16 ? nullptr : static_cast<const float*>(d_in),
+                                in_is_pcm16 ? static_cast<const int16_t*>(d_in) : nullptr, sr_in, d_in_starts, d_in_lengths,
+                                n_clips, max_in_len, d_out, d_out_starts, static_cast<cudaStream_t>(stream)));
+    return DYS_OK;
+}
+
+DYS_API int64_t dys_resample_table(int32_t sr_in, double* h_out, int64_t max_elems, int32_t* h_meta) {
+    return resample_table_host(sr_in, h_out, max_elems, h_meta);
+}
+
+}  // extern "C"
+
+namespace dys { namespace {
+
+int features_raw_impl(const float* d_audio, const int16_t* d_pcm, const int64_t* d_starts, const int32_t* d_lengths, int32_t n_clips,
+                      int32_t max_len, float* d_out, int32_t* d_status, void* d_workspace, int64_t workspace_bytes, void* stream) {
+    if (int rc = check_common(d_audio ? static_cast<const void*>(d_audio) : d_pcm, d_starts, d_lengths, n_clips, max_len)) return rc;
     if (n_clips == 0) return DYS_OK;
     if (!d_out || !d_status || !d_workspace) { set_error("null output / workspace pointer"); return DYS_ERR_INVALID; }
     const DeviceTables* tb = device_tables();
@@ -139,16 +197,16 @@ DYS_API int dys_features_raw(const float* d_audio, const int64_t* d_starts, cons
         return DYS_ERR_WORKSPACE;
     }
     ClipView cv{};
-    cv.audio = d_audio; cv.starts = d_starts; cv.lengths = d_lengths; cv.n_clips = n_clips; cv.max_len = max_len;
+    cv.audio = d_audio; cv.audio_q = d_pcm; cv.starts = d_starts; cv.lengths = d_lengths; cv.n_clips = n_clips; cv.max_len = max_len;
     return run_features(*tb, cv, n_clips, L, static_cast<unsigned char*>(d_workspace), size_t(workspace_bytes), d_out,
                         nullptr, d_status, static_cast<cudaStream_t>(stream));
 }
 
-DYS_API int dys_features_raw_clean(const float* d_audio, const int64_t* d_starts, const int32_t* d_lengths, int32_t n_clips,
-                           int32_t max_len, float prop_decrease, float* d_out_raw, float* d_out_clean,
-                           int32_t* d_status, int16_t* d_clean_pcm, const int64_t* d_pcm_starts, void* d_workspace,
-                           int64_t workspace_bytes, void* stream) {
-    if (int rc = check_common(d_audio, d_starts, d_lengths, n_clips, max_len)) return rc;
+int features_raw_clean_impl(const float* d_audio, const int16_t* d_pcm, const int64_t* d_starts, const int32_t* d_lengths,
+                            int32_t n_clips, int32_t max_len, float prop_decrease, float* d_out_raw, float* d_out_clean,
+                            int32_t* d_status, int16_t* d_clean_pcm, const int64_t* d_pcm_starts, void* d_workspace,
+                            int64_t workspace_bytes, void* stream) {
+    if (int rc = check_common(d_audio ? static_cast<const void*>(d_audio) : d_pcm, d_starts, d_lengths, n_clips, max_len)) return rc;
     if (n_clips == 0) return DYS_OK;
     if (!d_out_raw || !d_out_clean || !d_status || !d_workspace) {
         set_error("null output / workspace pointer");
@@ -170,7 +228,7 @@ DYS_API int dys_features_raw_clean(const float* d_audio, const int64_t* d_starts
     float* peak = reinterpret_cast<float*>(ws + L.peak_off);
     int32_t* flag = reinterpret_cast<int32_t*>(ws + L.flag_off);
     ClipView cv{};
-    cv.audio = d_audio; cv.starts = d_starts; cv.lengths = d_lengths; cv.n_clips = n_clips; cv.max_len = max_len;
+    cv.audio = d_audio; cv.audio_q = d_pcm; cv.starts = d_starts; cv.lengths = d_lengths; cv.n_clips = n_clips; cv.max_len = max_len;
     cv.clean = clean; cv.clean_pitch = L.clean_pitch; cv.clean_peak = peak; cv.clean_flag = flag; cv.clean_q = clean_q;
 
     // ---- spectral gate over sub-batches of chunks ------------------------------------------
@@ -192,6 +250,18 @@ DYS_API int dys_features_raw_clean(const float* d_audio, const int64_t* d_starts
     DYS_CUDA_OK(launch_quantize_pcm(cv, clean_q, d_clean_pcm, d_pcm_starts, st));
     // ---- features of both branches ----------------------------------------------------------
     return run_features(*tb, cv, 2 * n_clips, L, ws, size_t(workspace_bytes), d_out_raw, d_out_clean, d_status, st);
+}
+
+}}  // namespace dys::(anonymous)
+
+extern "C" {
+
+DYS_API int dys_features_raw_clean(const float* d_audio, const int64_t* d_starts, const int32_t* d_lengths, int32_t n_clips,
+                           int32_t max_len, float prop_decrease, float* d_out_raw, float* d_out_clean,
+                           int32_t* d_status, int16_t* d_clean_pcm, const int64_t* d_pcm_starts, void* d_workspace,
+                           int64_t workspace_bytes, void* stream) {
+    return features_raw_clean_impl(d_audio, nullptr, d_starts, d_lengths, n_clips, max_len, prop_decrease, d_out_raw, d_out_clean,
+                                   d_status, d_clean_pcm, d_pcm_starts, d_workspace, workspace_bytes, stream);
 }
 
 DYS_API int dys_cmvn_accumulate(const float* d_feats, int64_t n_rows, const double* d_shift, double* d_acc, double* d_partials,

@@ -138,9 +138,10 @@ __device__ __forceinline__ double2 split_factor(const LaneTrig& t) {
 
 // Windowed frame t of the zero-padded chunk -> STFT bins.  On return x[q] = D[lane + 32 q] (q < 16)
 // and *nyq = D[512] (real).
+template <bool kPcm>
 __device__ __forceinline__ void nr_frame_stft(const NrTables& sm, const NrFwdTables& fw, double2* xbuf,
-                                              const float* __restrict__ base, bool vec_ok, const NrGeom& g, int t, int lane,
-                                              double2 (&x)[16], double* nyq) {
+                                              const float* __restrict__ base, const int16_t* __restrict__ base_q, bool vec_ok,
+                                              const NrGeom& g, int t, int lane, double2 (&x)[16], double* nyq) {
     double2 v[16];
     const int p0 = t * kNrHop - kNrFft / 2;                 // padded-chunk coordinate of the frame's first sample
     static_for<16>([&](auto im) {
@@ -151,7 +152,15 @@ __device__ __forceinline__ void nr_frame_stft(const NrTables& sm, const NrFwdTab
         float a = 0.f, b = 0.f;
         const bool in0 = p >= 0 && p < g.L && s >= 0 && s < g.n;
         const bool in1 = p + 1 >= 0 && p + 1 < g.L && s + 1 >= 0 && s + 1 < g.n;
-        if (in0 && in1 && vec_ok) {
+        if constexpr (kPcm) {                               // int16 / 32768: exact in float32, like librosa.load on a 16-bit WAV
+            if (in0 && in1 && vec_ok) {
+                const short2 pr = __ldg(reinterpret_cast<const short2*>(base_q + s));
+                a = float(pr.x) * (1.0f / 32768.0f); b = float(pr.y) * (1.0f / 32768.0f);
+            } else {
+                if (in0) a = float(__ldg(base_q + s)) * (1.0f / 32768.0f);
+                if (in1) b = float(__ldg(base_q + s + 1)) * (1.0f / 32768.0f);
+            }
+        } else if (in0 && in1 && vec_ok) {
             const float2 pr = __ldg(reinterpret_cast<const float2*>(base + s));
             a = pr.x; b = pr.y;
         } else {
@@ -190,6 +199,7 @@ struct MagSmem {
     double2 xbuf[kWarps][kXbuf512];
 };
 
+template <bool kPcm>
 __global__ void __launch_bounds__(kThreads, 2)
 k_nr_stft_mag(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrScratch sc, int frames_per_cta) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -203,18 +213,23 @@ k_nr_stft_mag(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
     nr_load_tables(sm.tab, tb, tid, kThreads);
     nr_load_fwd_tables(sm.fwd, tb, tid, kThreads);
     __syncthreads();
-    const float* base = cv.audio + cv.starts[g.clip];
-    const bool vec_ok = (reinterpret_cast<uintptr_t>(base) & 7u) == 0 && (g.c0 & 1) == 0;
+    const float* base = kPcm ? nullptr : cv.audio + cv.starts[g.clip];
+    const int16_t* base_q = kPcm ? cv.audio_q + cv.starts[g.clip] : nullptr;
+    const bool vec_ok = (kPcm ? (reinterpret_cast<uintptr_t>(base_q) & 3u) == 0 : (reinterpret_cast<uintptr_t>(base) & 7u) == 0) &&
+                        (g.c0 & 1) == 0;
     double* mag = sc.mag + size_t(li) * sc.ta_max * kNrBinsPad;
     double2* spec = sc.spec + size_t(li) * sc.ta_max * kNrBinsPad;
     for (int t = t_begin + warp; t < t_end; t += kWarps) {
         {   // this warp's next frame starts 2048 samples further on: pull its 32 lines towards L2 while this one is transformed
             const long long s_next = (long long)(t + kWarps) * kNrHop - kNrFft / 2 - kNrPad + g.c0 + 32 * lane;
-            if (t + kWarps < t_end && s_next >= 0 && s_next < g.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + s_next));
+            if (t + kWarps < t_end && s_next >= 0 && s_next < g.n) {
+                if constexpr (kPcm) { if ((lane & 1) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(base_q + s_next)); }
+                else asm volatile("prefetch.global.L2 [%0];" ::"l"(base + s_next));
+            }
         }
         double2 x[16];
         double nyq;
-        nr_frame_stft(sm.tab, sm.fwd, sm.xbuf[warp], base, vec_ok, g, t, lane, x, &nyq);
+        nr_frame_stft<kPcm>(sm.tab, sm.fwd, sm.xbuf[warp], base, base_q, vec_ok, g, t, lane, x, &nyq);
         double* row = mag + size_t(t - g.t_first) * kNrBinsPad;
         double2* srow = spec + size_t(t - g.t_first) * kNrBinsPad;
         static_for<16>([&](auto iq) {
@@ -638,9 +653,9 @@ __global__ void k_quantize_pcm(const ClipView cv, int16_t* __restrict__ clean_q,
     int16_t* user = pcm ? pcm + pcm_starts[c] : nullptr;
     if (cv.clean_flag[c] != 0) {           // reference wrote no WAV for this clip; the caller's buffer gets the raw samples quantised
         if (!user) return;
-        const float* src = cv.audio + cv.starts[c];
         for (int i = blockIdx.y * blockDim.x + threadIdx.x; i < n; i += gridDim.y * blockDim.x) {
-            float q = rintf(src[i] * 32768.0f);
+            if (cv.audio_q) { user[i] = cv.audio_q[cv.starts[c] + i]; continue; }
+            float q = rintf(cv.audio[cv.starts[c] + i] * 32768.0f);
             user[i] = int16_t(fminf(fmaxf(q, -32768.0f), 32767.0f));
         }
         return;
@@ -705,7 +720,8 @@ cudaError_t launch_clean_init(const ClipView& cv, float* clean_peak, int32_t* cl
 cudaError_t launch_denoise(const DeviceTables& tb, const ClipView& cv, float* clean, float* clean_peak, int32_t* clean_flag,
                            int cpc, int item0, int n_items, const NrScratch& sc, float prop_decrease, cudaStream_t stream) {
     if (n_items <= 0) return cudaSuccess;
-    if (cudaError_t e = ensure_dynamic_smem<kK_nr_stft_mag>(k_nr_stft_mag, int(sizeof(MagSmem)))) return e;
+    if (cudaError_t e = ensure_dynamic_smem<kK_nr_stft_mag>(k_nr_stft_mag<false>, int(sizeof(MagSmem)))) return e;
+    if (cudaError_t e = ensure_dynamic_smem<kK_nr_stft_mag + 32>(k_nr_stft_mag<true>, int(sizeof(MagSmem)))) return e;
     if (cudaError_t e = ensure_dynamic_smem<kK_nr_apply_ola>(k_nr_apply_ola<kApplyWarps>, int(sizeof(ApplySmem<kApplyWarps>)))) return e;
     if (sc.ta_max > kIirMaxCk << kIirCkShift) return cudaErrorInvalidValue;
     const bool big = n_items >= kBigGroup;
@@ -714,7 +730,8 @@ cudaError_t launch_denoise(const DeviceTables& tb, const ClipView& cv, float* cl
     ClipView cvw = cv;
     cvw.clean = clean; cvw.clean_peak = clean_peak; cvw.clean_flag = clean_flag;
     { LaunchScope ls(kK_nr_stft_mag, stream);
-      k_nr_stft_mag<<<dim3(n_items, gy), kThreads, sizeof(MagSmem), stream>>>(tb, cvw, cpc, item0, sc, fpc); }
+      if (cv.audio_q) k_nr_stft_mag<true><<<dim3(n_items, gy), kThreads, sizeof(MagSmem), stream>>>(tb, cvw, cpc, item0, sc, fpc);
+      else k_nr_stft_mag<false><<<dim3(n_items, gy), kThreads, sizeof(MagSmem), stream>>>(tb, cvw, cpc, item0, sc, fpc); }
     { LaunchScope ls(kK_nr_iir_mask, stream);
       k_nr_iir_mask<<<dim3(n_items, (kNrBins + kIirThreads - 1) / kIirThreads), kIirThreads, 0, stream>>>(tb, cvw, cpc, item0, sc,
                                                                                                       clean_flag); }

@@ -40,9 +40,10 @@ __device__ __forceinline__ float dec_f32(int i) { return __int_as_float(i >= 0 ?
 
 struct InstSrc {
     const float* f32;    // float32 samples of the clip on this branch (raw clip, or raw clip as clean fallback) ...
-    const int16_t* q16;  // ... or the PCM-16 the reference would have written to clear_audio/<stem>.wav (clean branch)
+    const int16_t* q16;  // ... or PCM-16: the caller's 16-bit samples, or what the reference would have written to
+                         //     clear_audio/<stem>.wav (clean branch)
     int n;               // samples
-    bool vec_ok;         // f32 is 8-byte aligned
+    bool vec_ok;         // the active source allows the vector loads (f32: 8-byte aligned, q16: 4-byte aligned)
 };
 
 __device__ __forceinline__ InstSrc inst_source(const ClipView& cv, int inst) {
@@ -52,10 +53,10 @@ __device__ __forceinline__ InstSrc inst_source(const ClipView& cv, int inst) {
     int n = cv.lengths[c];
     if (n < 0 || n > cv.max_len) n = 0;
     s.n = n;
-    s.f32 = cv.audio + cv.starts[c];
-    s.q16 = nullptr;
+    s.f32 = cv.audio ? cv.audio + cv.starts[c] : nullptr;
+    s.q16 = cv.audio_q ? cv.audio_q + cv.starts[c] : nullptr;
     if (clean && cv.clean_flag[c] == 0) s.q16 = cv.clean_q + int64_t(c) * cv.clean_pitch;
-    s.vec_ok = (reinterpret_cast<uintptr_t>(s.f32) & 7u) == 0;
+    s.vec_ok = s.q16 ? (reinterpret_cast<uintptr_t>(s.q16) & 3u) == 0 : (reinterpret_cast<uintptr_t>(s.f32) & 7u) == 0;
     return s;
 }
 
@@ -144,7 +145,7 @@ k_frame_spectra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
             }
         }
         float2 v[32];
-        if (interior && src.q16) {                          // clean branch: int16 / 32768 (exact), as librosa.load reads the WAV
+        if (interior && src.q16 && src.vec_ok) {            // PCM-16: int16 / 32768 (exact), as librosa.load reads a 16-bit WAV
             const short2* q2 = reinterpret_cast<const short2*>(src.q16 + f0);
             short2 raw[32];
             static_for<32>([&](auto im) { constexpr int m = decltype(im)::value; raw[m] = __ldg(q2 + lane + 32 * m); });
@@ -152,7 +153,7 @@ k_frame_spectra(const DeviceTables tb, const ClipView cv, int inst0, FeatScratch
                 constexpr int m = decltype(im)::value;
                 v[m] = vmul(make_float2(float(raw[m].x), float(raw[m].y)), hann2[lane + 32 * m]);   // x 2^15, undone at the power
             });
-        } else if (interior && src.vec_ok) {
+        } else if (interior && !src.q16 && src.vec_ok) {
             const float2* x2 = reinterpret_cast<const float2*>(src.f32 + f0);
             static_for<32>([&](auto im) { constexpr int m = decltype(im)::value; v[m] = __ldg(x2 + lane + 32 * m); });
             static_for<32>([&](auto im) {

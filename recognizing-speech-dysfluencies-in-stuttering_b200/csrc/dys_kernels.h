@@ -37,7 +37,8 @@ __host__ __device__ inline int frames_of(int n) { return 1 + n / kHop; }
 // One "instance" = one clip on one branch (raw or clean).  Instances [0, n_clips) are the raw
 // branch, [n_clips, 2 n_clips) the clean branch of clip (i - n_clips).
 struct ClipView {
-    const float* audio;          // raw samples (packed buffer)
+    const float* audio;          // raw samples (packed buffer), float32 ...
+    const int16_t* audio_q;      // ... or PCM-16 (value = q / 32768, what librosa.load returns for a 16-bit WAV); one of the two is null
     const int64_t* starts;       // [n_clips] first sample of clip c in `audio`
     const int32_t* lengths;      // [n_clips]
     int n_clips;
@@ -111,5 +112,13 @@ cudaError_t launch_cmvn_accumulate(const float* feats, int64_t n_rows, const dou
 cudaError_t launch_cmvn_finalize(const double* acc, const double* shift, double* mean, double* scale, cudaStream_t stream);
 cudaError_t launch_cmvn_apply(const float* feats, int64_t n_rows, const double* mean, const double* scale, float* out,
                               cudaStream_t stream);
+
+// Rate conversion sr_in -> 16 kHz (librosa.load's soxr_hq step, pipeline1.py:102).  in_f32 / in_q16: one of the two is null.
+// Clip c: n_in = in_lengths[c] samples at in_starts[c] -> ceil(n_in * 16000 / sr_in) float32 samples at out_starts[c].
+cudaError_t launch_resample(const float* in_f32, const int16_t* in_q16, int sr_in, const int64_t* in_starts,
+                            const int32_t* in_lengths, int n_clips, int max_in_len, float* out, const int64_t* out_starts,
+                            cudaStream_t stream);
+// Host copy of the polyphase table for the parity tests: returns up * ntaps (0 when sr_in is unsupported); meta = {up, down, half, ntaps}.
+int64_t resample_table_host(int sr_in, double* h_out, int64_t max_elems, int32_t* meta);
 
 }  // namespace dys

@@ -12,7 +12,7 @@ const char* const kNames[kKernelCount] = {
     "k_feat_init", "k_frame_spectra", "k_tuning", "k_frame_cepstra", "k_clip_stats", "k_clean_init",
     "k_nr_stft_mag", "k_nr_iir_mask", "k_nr_apply_ola", "k_quantize_pcm",
     "k_cmvn_partial", "k_cmvn_merge", "k_cmvn_finalize", "k_cmvn_apply",
-    "k_qc_snr", "k_qc_hf_bins", "k_qc_finish", "k_qc_flatness", "k_qc_flat_reduce"};
+    "k_qc_snr", "k_qc_hf_bins", "k_qc_finish", "k_qc_flatness", "k_qc_flat_reduce", "k_resample"};
 
 struct Record {
     int id;

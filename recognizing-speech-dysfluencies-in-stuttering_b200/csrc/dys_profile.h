@@ -29,6 +29,7 @@ enum KernelId : int {
     kK_qc_finish,
     kK_qc_flatness,
     kK_qc_flat_reduce,
+    kK_resample,
     kKernelCount
 };
 

@@ -27,7 +27,7 @@ from typing import Sequence
 import numpy as np
 import torch
 
-from . import _lib, wavio
+from . import _lib, mp3io, wavio
 from ._lib import AUDIO_FEATURE_LEN, FEATURE_LEN, SAMPLE_RATE, STATUS_CLEAN_FALLBACK, DysError
 
 # same module-level knobs as the reference (pipeline1.py:29-32, 77-86)
@@ -57,22 +57,31 @@ def _device(device=None) -> torch.device:
 
 
 class _Arena:
-    """Grow-only uint8 scratch tensor per (device, slot); slots let two streams work concurrently."""
+    """Grow-only uint8 scratch tensor per (device, slot, stream).  Work queued on different streams never shares a
+    buffer (two asynchronous calls on two streams would otherwise race on the denoised clips and the scratch); a buffer
+    that is replaced by a larger one is handed back to the caching allocator only after the stream that used it has
+    passed this point (record_stream)."""
 
     def __init__(self):
         self._bufs: dict = {}
 
+    @staticmethod
+    def _key(device: torch.device, slot: int):
+        return (device.index, slot, int(torch.cuda.current_stream(device).cuda_stream))
+
     def get(self, device: torch.device, nbytes: int, slot: int = 0) -> torch.Tensor:
-        key = (device.index, slot)
+        key = self._key(device, slot)
         buf = self._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
+            if buf is not None:
+                buf.record_stream(torch.cuda.current_stream(device))
             self._bufs[key] = None
             buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
             self._bufs[key] = buf
         return buf
 
     def size(self, device: torch.device, slot: int = 0) -> int:
-        buf = self._bufs.get((device.index, slot))
+        buf = self._bufs.get(self._key(device, slot))
         return 0 if buf is None else int(buf.numel())
 
     def clear(self):
@@ -80,6 +89,7 @@ class _Arena:
 
 
 _arena = _Arena()
+abi_calls = {"features": 0}          # C-ABI feature calls issued by this module (tests: the run-in-pieces path)
 
 
 def release_workspaces():
@@ -87,11 +97,16 @@ def release_workspaces():
     _arena.clear()
 
 
-def _workspace_limit(dev: torch.device) -> int:
-    """Largest workspace one C-ABI call may ask for: DYS_MAX_WORKSPACE_MB, else half of the free device memory."""
+def _workspace_limit(dev: torch.device, full: int, slot: int) -> int | None:
+    """Largest workspace one C-ABI call may ask for, or None for "no limit applies".  DYS_MAX_WORKSPACE_MB is always
+    honoured when set.  Otherwise half of the free device memory -- but cudaMemGetInfo is a slow, occasionally blocking
+    driver query, so it is only asked when a workspace above 1 GiB would have to be allocated (the 400-clip chunks of
+    the host streaming path never are)."""
     env = os.environ.get("DYS_MAX_WORKSPACE_MB")
     if env:
         return max(1, int(env)) << 20
+    if full <= (1 << 30) or _arena.size(dev, slot) >= full:
+        return None
     free, _ = torch.cuda.mem_get_info(dev)
     return max(free // 2, 1 << 28)
 
@@ -115,12 +130,10 @@ def _run_device(d_audio: torch.Tensor, d_starts: torch.Tensor, d_lengths: torch.
         pcm = pcm_out if pcm_out is not None else (
             torch.empty((total_pcm,), dtype=torch.int16, device=dev) if (denoise and want_pcm) else None)
         piece = n
-        # cudaMemGetInfo is a slow, occasionally blocking driver query: only ask when the workspace is big enough to matter
-        # (the 400-clip chunks of the host streaming path never are)
         full = lib.dys_workspace_bytes(n, max_len, flag)
-        if workspace_bytes is None and n > 1 and full > (1 << 30) and _arena.size(dev, slot) < full:
-            limit = _workspace_limit(dev)                       # only when a larger arena would have to be allocated
-            if full > limit:
+        if workspace_bytes is None and n > 1:
+            limit = _workspace_limit(dev, full, slot)
+            if limit is not None and full > limit:
                 lo, hi = 1, n                                   # largest piece whose workspace fits (monotone in the count)
                 while lo < hi:
                     mid = (lo + hi + 1) // 2
@@ -131,15 +144,19 @@ def _run_device(d_audio: torch.Tensor, d_starts: torch.Tensor, d_lengths: torch.
                 piece = lo
         need = lib.dys_workspace_bytes(piece, max_len, flag) if workspace_bytes is None else workspace_bytes
         ws = _arena.get(dev, max(int(need), 256), slot)
+        pcm_in = d_audio.dtype == torch.int16                   # 16-bit samples: value = q / 32768 (librosa.load on a PCM-16 WAV)
+        f_raw = lib.dys_features_raw_pcm16 if pcm_in else lib.dys_features_raw
+        f_both = lib.dys_features_raw_clean_pcm16 if pcm_in else lib.dys_features_raw_clean
         for i0 in range(0, n, piece):
             m = min(piece, n - i0)
             st = status if m == n else torch.empty(((2 if denoise else 1) * m,), dtype=torch.int32, device=dev)
+            abi_calls["features"] += 1
             if not denoise:
-                _lib.check(lib.dys_features_raw(d_audio.data_ptr(), d_starts[i0:].data_ptr(), d_lengths[i0:].data_ptr(), m,
+                _lib.check(f_raw(d_audio.data_ptr(), d_starts[i0:].data_ptr(), d_lengths[i0:].data_ptr(), m,
                                                 max_len, raw[i0:].data_ptr(), st.data_ptr(), ws.data_ptr(), int(need), stream),
                            "dys_features_raw")
             else:
-                _lib.check(lib.dys_features_raw_clean(d_audio.data_ptr(), d_starts[i0:].data_ptr(), d_lengths[i0:].data_ptr(), m,
+                _lib.check(f_both(d_audio.data_ptr(), d_starts[i0:].data_ptr(), d_lengths[i0:].data_ptr(), m,
                                                       max_len, float(prop_decrease), raw[i0:].data_ptr(), clean[i0:].data_ptr(),
                                                       st.data_ptr(), pcm.data_ptr() if pcm is not None else None,
                                                       d_pcm_starts[i0:].data_ptr() if pcm is not None else None,
@@ -203,19 +220,32 @@ def _run_length_binned(d_audio, d_starts, d_lens, h_lens: np.ndarray, denoise: b
     return raw, clean, status, pcm
 
 
-def _pack_host(clips: Sequence) -> tuple[torch.Tensor, np.ndarray, np.ndarray, int]:
-    """Packs variable-length host clips into one pinned float32 buffer; clip starts are 4-sample aligned."""
+def _all_int16(clips: Sequence) -> bool:
+    seen = False
+    for c in clips:
+        if c is None:
+            continue
+        dt = c.dtype if isinstance(c, (np.ndarray, torch.Tensor)) else None
+        if dt not in (np.dtype(np.int16), torch.int16):
+            return False
+        seen = True
+    return seen
+
+
+def _pack_host(clips: Sequence, pcm16: bool = False) -> tuple[torch.Tensor, np.ndarray, np.ndarray, int]:
+    """Packs variable-length host clips into one pinned buffer (float32, or int16 for PCM-16 clips); clip starts are
+    4-sample aligned."""
     lens = np.asarray([0 if c is None else int(np.asarray(c).shape[0]) for c in clips], dtype=np.int64)
     padded = (lens + 3) & ~3
     starts = np.zeros(len(clips), dtype=np.int64)
     if len(clips) > 1:
         starts[1:] = np.cumsum(padded)[:-1]
     total = int(padded.sum()) if len(clips) else 0
-    buf = torch.zeros(max(total, 4), dtype=torch.float32).pin_memory()
+    buf = torch.zeros(max(total, 4), dtype=torch.int16 if pcm16 else torch.float32).pin_memory()
     view = buf.numpy()
     for c, s, n in zip(clips, starts, lens):
         if n:
-            view[s:s + n] = np.asarray(c, dtype=np.float32).reshape(-1)
+            view[s:s + n] = np.asarray(c, dtype=np.int16 if pcm16 else np.float32).reshape(-1)
     return buf, starts, lens.astype(np.int32), int(lens.max()) if len(clips) else 0
 
 
@@ -231,6 +261,8 @@ def extract_features_batch(audio, lengths=None, starts=None, sr: int = TARGET_SR
             * 2-D [B, n] numpy / torch tensor (CPU or CUDA) of equal-length clips, or
             * 1-D CUDA/CPU tensor of packed samples with ``starts`` (int64[B]) and ``lengths`` (int32[B]);
               windows may overlap (long-form sliding windows need no copy).
+            int16 input (every clip of a list, or the tensor) is taken as PCM-16, value = q / 32768 -- what
+            ``librosa.load`` returns for a 16-bit WAV -- and stays 16-bit all the way into the kernels.
     denoise False -> raw[B,149];  True -> (raw[B,149], clean[B,149]) where clean goes through the
             reference's spectral gate, peak normalisation and PCM-16 round trip.
     Returns CUDA float32 tensors (plus int32 status [B] or [2B], plus a list of int16 PCM tensors).
@@ -241,17 +273,23 @@ def extract_features_batch(audio, lengths=None, starts=None, sr: int = TARGET_SR
     dev = _device(device if device is not None else (audio.device if isinstance(audio, torch.Tensor) and audio.is_cuda else None))
     with torch.cuda.device(dev):
         if isinstance(audio, (list, tuple)):
-            host, h_starts, h_lens, max_len = _pack_host(audio)
+            host, h_starts, h_lens, max_len = _pack_host(audio, pcm16=_all_int16(audio))
             d_audio = host.to(dev, non_blocking=True)
         else:
-            t = audio if isinstance(audio, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(audio, dtype=np.float32))
-            if t.dtype != torch.float32:
+            if isinstance(audio, torch.Tensor):
+                t = audio
+            else:
+                a = np.asarray(audio)
+                t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.int16 if a.dtype == np.int16 else np.float32))
+            if t.dtype not in (torch.float32, torch.int16):
                 t = t.float()
             if t.dim() == 2:
                 B, n = t.shape
                 t = t.contiguous()
                 h_starts = np.arange(B, dtype=np.int64) * n
                 h_lens = np.full(B, n, dtype=np.int32) if lengths is None else np.asarray(lengths, dtype=np.int32)
+                if len(h_lens) != B or (B and (h_lens.min() < 0 or h_lens.max() > n)):
+                    raise ValueError("lengths must hold one value in [0, n] per row of the [B, n] batch")
                 max_len = n
                 d_audio = t.reshape(-1).to(dev, non_blocking=True)
             elif t.dim() == 1 and starts is not None and lengths is not None:
@@ -310,11 +348,13 @@ def extract_features_host(audio: torch.Tensor, denoise: bool = True, prop_decrea
     chunk's kernels fill the idle tail of its predecessor's, which is what makes small chunks efficient (measured on
     B200, 10 000 3-s clips: 42.6 ms with one compute stream and 1250-clip chunks, 39.9 ms with two streams and 625,
     37.8 ms with three and 400; the copy alone takes 34.5 ms, the kernels alone 34.4 ms)."""
-    if audio.is_cuda or audio.dim() != 2 or audio.dtype != torch.float32:
-        raise ValueError("audio must be a 2-D float32 CPU tensor [B, n]")
+    if audio.is_cuda or audio.dim() != 2 or audio.dtype not in (torch.float32, torch.int16):
+        raise ValueError("audio must be a 2-D float32 or int16 (PCM-16) CPU tensor [B, n]")
     prop = PROP_DECREASE if prop_decrease is None else float(prop_decrease)
     dev = _device(device)
     B, n = audio.shape
+    pcm_in = audio.dtype == torch.int16           # half the bytes over PCIe; bit-identical to feeding int16 / 32768.0f
+    esz = 2 if pcm_in else 4
     if out_raw is None:
         out_raw = torch.empty((B, FEATURE_LEN), dtype=torch.float32).pin_memory()
     if denoise and out_clean is None:
@@ -330,12 +370,14 @@ def extract_features_host(audio: torch.Tensor, denoise: bool = True, prop_decrea
     n_comp = max(1, min(int(compute_streams), 4))
     lib = _lib.load()
     flag = 1 if denoise else 0
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _host_lock:
         _lib.check(lib.dys_init(), "dys_init")
         cur = torch.cuda.current_stream(dev)
         streams = _host_streams(dev, 1 + n_comp)
         copy_s, comp = streams[0], streams[1:]
-        staging = _arena.get(dev, B * n * 4, slot=10).view(torch.float32)[:B * n]
+        staging = _arena.get(dev, B * n * esz, slot=10)[:B * n * esz].view(audio.dtype)
+        f_both = lib.dys_features_raw_clean_pcm16 if pcm_in else lib.dys_features_raw_clean
+        f_raw = lib.dys_features_raw_pcm16 if pcm_in else lib.dys_features_raw
         biggest = max(sizes)
         base_starts = (torch.arange(biggest, dtype=torch.int64) * n).to(dev)
         base_lens = torch.full((biggest,), n, dtype=torch.int32, device=dev)
@@ -368,12 +410,11 @@ def extract_features_host(audio: torch.Tensor, denoise: bool = True, prop_decrea
             with torch.cuda.stream(s):
                 s.wait_event(ev)
                 if denoise:
-                    rc = lib.dys_features_raw_clean(in_ptr + c0 * n * 4, st_ptr, ln_ptr, cnt, n, prop, raw_k.data_ptr(),
-                                                    clean_k.data_ptr(), st_k.data_ptr(), None, None, ws.data_ptr(), need,
-                                                    s.cuda_stream)
+                    rc = f_both(in_ptr + c0 * n * esz, st_ptr, ln_ptr, cnt, n, prop, raw_k.data_ptr(),
+                                clean_k.data_ptr(), st_k.data_ptr(), None, None, ws.data_ptr(), need, s.cuda_stream)
                 else:
-                    rc = lib.dys_features_raw(in_ptr + c0 * n * 4, st_ptr, ln_ptr, cnt, n, raw_k.data_ptr(), st_k.data_ptr(),
-                                              ws.data_ptr(), need, s.cuda_stream)
+                    rc = f_raw(in_ptr + c0 * n * esz, st_ptr, ln_ptr, cnt, n, raw_k.data_ptr(), st_k.data_ptr(),
+                               ws.data_ptr(), need, s.cuda_stream)
                 _lib.check(rc, "dys_features_raw_clean" if denoise else "dys_features_raw")
                 out_raw[c0:c0 + cnt].copy_(raw_k[:cnt], non_blocking=True)
                 if denoise:
@@ -423,6 +464,7 @@ def extract_features_longform(recording, win: int = 48000, hop: int = 24000, den
 
 
 _streams: dict = {}
+_host_lock = __import__("threading").RLock()      # the host streaming paths own fixed streams and arena slots: one call at a time
 
 
 def _host_streams(dev: torch.device, count: int = 2):
@@ -435,17 +477,106 @@ def _host_streams(dev: torch.device, count: int = 2):
 # ------------------------------------------------------------------------------------------
 # the reference's single-clip interface
 # ------------------------------------------------------------------------------------------
+def resample_to_16k(clips: Sequence, sr_in: int, device=None, return_device: bool = False):
+    """The rate-conversion half of ``librosa.load(path, sr=16000)`` (pipeline1.py:102) for a batch of mono clips at
+    ``sr_in`` Hz (float32, or int16 PCM): one H2D copy, one kernel (soxr "HQ" restated, see dys_resample.cu), clip i
+    comes back with ``ceil(len_i * 16000 / sr_in)`` float32 samples.  ``return_device`` -> (packed CUDA float32 buffer,
+    int64 starts, int32 lengths) ready for ``extract_features_batch(buf, starts=..., lengths=...)`` without a host trip."""
+    lib = _lib.load()
+    dev = _device(device)
+    if sr_in == TARGET_SR:
+        raise ValueError("clips are already at 16 kHz")
+    pcm16 = _all_int16(clips)
+    with torch.cuda.device(dev):
+        _lib.check(lib.dys_init(), "dys_init")
+        host, h_starts, h_lens, max_len = _pack_host(clips, pcm16=pcm16)
+        out_lens = np.asarray([lib.dys_resampled_length(int(n), int(sr_in)) for n in h_lens], dtype=np.int64)
+        if len(out_lens) and out_lens.min() < 0:
+            raise ValueError(f"unsupported sample rate {sr_in}")
+        padded = (out_lens + 3) & ~3
+        o_starts = np.zeros(len(clips), dtype=np.int64)
+        if len(clips) > 1:
+            o_starts[1:] = np.cumsum(padded)[:-1]
+        total = int(padded.sum()) if len(clips) else 0
+        d_in = host.to(dev, non_blocking=True)
+        d_is = torch.from_numpy(h_starts).to(dev, non_blocking=True)
+        d_il = torch.from_numpy(np.ascontiguousarray(h_lens)).to(dev, non_blocking=True)
+        d_os = torch.from_numpy(o_starts).to(dev, non_blocking=True)
+        d_out = torch.zeros(max(total, 4), dtype=torch.float32, device=dev)
+        if len(clips) and max_len > 0:
+            _lib.check(lib.dys_resample_to_16k(d_in.data_ptr(), 1 if pcm16 else 0, int(sr_in), d_is.data_ptr(), d_il.data_ptr(),
+                                               len(clips), int(max_len), d_out.data_ptr(), d_os.data_ptr(),
+                                               torch.cuda.current_stream(dev).cuda_stream), "dys_resample_to_16k")
+        for t in (d_in, d_is, d_il, d_os):
+            t.record_stream(torch.cuda.current_stream(dev))
+        if return_device:
+            return d_out, o_starts, out_lens.astype(np.int32)
+        h = d_out.cpu().numpy()
+        return [h[s:s + n].copy() for s, n in zip(o_starts, out_lens)]
+
+
+def _decode_file(path: str):
+    """-> (mono samples at the file's own rate: float32, or int16 for PCM-16 WAV; sample rate)."""
+    ext = os.path.splitext(path)[1].lower()
+    if ext == ".mp3":
+        return mp3io.read_mp3(path)
+    if ext == ".wav":
+        return wavio.read_wav_pcm16(path)
+    raise ValueError(f"unsupported audio format {ext!r} (WAV/PCM-16 and MP3 are decoded here)")
+
+
 def load_audio(path: str, sr: int = TARGET_SR):
-    """pipeline1.py:100-106.  Returns (float32[n], sr) or (None, None) after logging.  Only 16 kHz mono
-    PCM-16 WAV is decoded here (decode/resample of other formats is upstream of this package)."""
+    """pipeline1.py:100-106: ``librosa.load(path, sr=16000, mono=True)``.  Returns (float32[n], sr) or (None, None)
+    after logging.  Mono PCM-16 WAV and MPEG Layer III are decoded on the host (file I/O); a file whose own rate is not
+    ``sr`` -- the reference's whole MP3 corpus is 22 050 Hz -- is converted on the GPU (``resample_to_16k``)."""
+    if sr != TARGET_SR:
+        raise ValueError(f"only sr={TARGET_SR} is supported (the reference always passes TARGET_SR)")
     try:
-        y, s = wavio.read_wav(path)
+        y, s = _decode_file(path)
+        if y.dtype == np.int16 and s == sr:
+            return (y.astype(np.float32) / np.float32(32768.0)), s
         if s != sr:
-            raise ValueError(f"sample rate {s} != {sr}: resampling is upstream of this package")
-        return y, s
+            y = resample_to_16k([y], s)[0]
+        return np.asarray(y, dtype=np.float32), sr
+    except DysError:
+        raise
     except Exception as e:  # noqa: BLE001 - mirrors the reference's blanket handler
         logging.error(f"load_audio fail {path}: {e}")
         return None, None
+
+
+def load_audio_batch(paths: Sequence[str], io_threads: int = 8):
+    """``load_audio`` for many files: decoding runs on a thread pool, rate conversion as one GPU batch per source
+    rate.  -> list of float32 arrays (``None`` where the reference's ``load_audio`` would return ``(None, None)``)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    def dec(p):
+        try:
+            return _decode_file(p)
+        except Exception as e:  # noqa: BLE001
+            logging.error(f"load_audio fail {p}: {e}")
+            return None
+    with ThreadPoolExecutor(max_workers=max(1, io_threads)) as pool:
+        decoded = list(pool.map(dec, paths))
+    out = [None] * len(paths)
+    by_rate: dict = {}
+    for i, d in enumerate(decoded):
+        if d is None:
+            continue
+        y, s = d
+        if s == TARGET_SR:
+            out[i] = (y.astype(np.float32) / np.float32(32768.0)) if y.dtype == np.int16 else np.asarray(y, np.float32)
+        else:
+            by_rate.setdefault((s, y.dtype == np.int16), []).append(i)
+    for (s, _), idx in by_rate.items():
+        try:
+            for i, y in zip(idx, resample_to_16k([decoded[i][0] for i in idx], s)):
+                out[i] = y
+        except DysError:
+            raise
+        except Exception as e:  # noqa: BLE001
+            logging.error(f"load_audio fail ({len(idx)} files at {s} Hz): {e}")
+    return out
 
 
 def repetition_stats_from_text(text: str):
@@ -543,7 +674,7 @@ def cached_extract_features(path: str, transcript: str, suffix: str) -> np.ndarr
     base = os.path.basename(path).rsplit(".", 1)[0]
     cache_file = os.path.normpath(os.path.join(CACHE_DIR, f"{base}_{suffix}_feats.npy"))
     try:
-        return np.array(np.load(cache_file, allow_pickle=True))
+        return np.array(np.load(cache_file, allow_pickle=False))      # same files; no unpickling of a shared cache directory
     except Exception:  # noqa: BLE001
         pass
     y, sr = load_audio(path, sr=TARGET_SR)
@@ -559,15 +690,17 @@ def _stem(path: str) -> str:
 
 def build_feature_cache(paths: Sequence[str], overwrite: bool = False, io_threads: int = 8):
     """Batched replacement for the reference's two per-file loops (pipeline1.py:371-417 and :447-453): loads every
-    readable clip, runs ONE raw+clean batch on the GPU and writes the artefacts the reference writes --
-    CLEAR_DIR/<stem>.wav, CACHE_DIR/<stem>_raw_feats.npy, CACHE_DIR/<stem>_clean_feats.npy (byte-identical .npy
-    headers: np.save of float32 (149,)); file writes run on a thread pool while the next results are prepared.
+    readable file (WAV or MP3, any rate: ``load_audio_batch``), runs batched GPU passes and writes the artefacts the
+    reference writes -- CLEAR_DIR/<stem>.wav, CACHE_DIR/<stem>_raw_feats.npy, CACHE_DIR/<stem>_clean_feats.npy
+    (byte-identical .npy headers: np.save of float32 (149,)); file writes run on a thread pool.
 
-    The reference's caches are keyed by the basename stem only (pipeline1.py:132, :432), so two inputs with the
-    same stem alias: the second one reuses the first one's WAV and cached vectors (16 stems of the corpus do).
-    That is reproduced: an entry already on disk (unless ``overwrite``) or produced earlier in this call is what
-    the row of X_before / X_after holds, exactly like ``cached_extract_features``' hit path, and such clips are
-    not sent to the GPU at all.  Returns (X_before, X_after, kept_paths)."""
+    Cache semantics are the reference's, artefact by artefact (unless ``overwrite``):
+      * an existing CLEAR_DIR/<stem>.wav is reused as it is (pipeline1.py:134-135) -- and a missing clean vector is then
+        computed FROM THAT FILE (pipeline1.py:437 loads the WAV), not from a fresh denoise, so WAV and vector agree;
+      * an existing ``_raw_feats.npy`` / ``_clean_feats.npy`` is loaded, never rewritten (pipeline1.py:434-436);
+      * caches are keyed by the basename stem only (pipeline1.py:132, :432), so two inputs with the same stem alias:
+        the second one reuses the first one's artefacts (16 stems of the corpus do).
+    Returns (X_before, X_after, kept_paths)."""
     from concurrent.futures import ThreadPoolExecutor
 
     def files_of(stem):
@@ -575,23 +708,14 @@ def build_feature_cache(paths: Sequence[str], overwrite: bool = False, io_thread
                 os.path.normpath(os.path.join(CACHE_DIR, f"{stem}_raw_feats.npy")),
                 os.path.normpath(os.path.join(CACHE_DIR, f"{stem}_clean_feats.npy")))
 
-    kept, clips, owner = [], [], {}                    # owner: stem -> index into `clips` (first occurrence computes)
-    rows = []                                          # per kept path: ("disk", stem) | ("gpu", clip index)
-    for p in paths:
-        y, _ = load_audio(p, sr=TARGET_SR)
+    loaded = load_audio_batch(paths, io_threads)
+    kept, stems, first = [], [], {}                    # first: stem -> its first clip (the one whose artefacts everybody shares)
+    for p, y in zip(paths, loaded):
         if y is None:
             continue                                   # reference: skipped += 1
         kept.append(p)
-        stem = _stem(p)
-        _, f_raw, f_clean = files_of(stem)
-        if stem in owner:
-            rows.append(("gpu", owner[stem]))
-        elif not overwrite and os.path.exists(f_raw) and os.path.exists(f_clean):
-            rows.append(("disk", stem))
-        else:
-            owner[stem] = len(clips)
-            clips.append(y)
-            rows.append(("gpu", owner[stem]))
+        stems.append(_stem(p))
+        first.setdefault(stems[-1], y)
     n = len(kept)
     Xb = np.empty((n, FEATURE_LEN), np.float32)
     Xa = np.empty((n, FEATURE_LEN), np.float32)
@@ -599,26 +723,52 @@ def build_feature_cache(paths: Sequence[str], overwrite: bool = False, io_thread
         return Xb, Xa, []
     os.makedirs(CLEAR_DIR, exist_ok=True)
     os.makedirs(CACHE_DIR, exist_ok=True)
-    raw = clean = status = pcm = None
-    if clips:
-        raw, clean, status, pcm = extract_features_batch(clips, denoise=True, return_status=True, return_pcm=True)
-        raw, clean, status = raw.cpu().numpy(), clean.cpu().numpy(), status.cpu().numpy()
+    gate, raw_only, from_wav = [], [], []              # stems per GPU pass
+    for stem in first:
+        wav, f_raw, f_clean = files_of(stem)
+        have_wav = os.path.exists(wav) and not overwrite
+        need_raw = overwrite or not os.path.exists(f_raw)
+        need_clean = overwrite or not os.path.exists(f_clean)
+        if not have_wav:
+            gate.append(stem)                          # the reference's loop A would denoise and write the WAV
+        else:
+            if need_raw:
+                raw_only.append(stem)
+            if need_clean:
+                from_wav.append(stem)
+    vec_raw, vec_clean, jobs = {}, {}, []
     with ThreadPoolExecutor(max_workers=max(1, io_threads)) as pool:
-        jobs = []
-        for stem, ci in owner.items():
-            wav, f_raw, f_clean = files_of(stem)
-            if status[len(clips) + ci] & STATUS_CLEAN_FALLBACK:
-                logging.error(f"clean_audio fail {stem}: Input must be finite")
-            elif overwrite or not os.path.exists(wav):
-                jobs.append(pool.submit(wavio.write_wav_pcm16, wav, pcm[ci].cpu().numpy(), TARGET_SR))
-            jobs.append(pool.submit(np.save, f_raw, raw[ci]))
-            jobs.append(pool.submit(np.save, f_clean, clean[ci]))
-        for i, (kind, ref) in enumerate(rows):
-            if kind == "gpu":
-                Xb[i], Xa[i] = raw[ref], clean[ref]
-            else:
-                _, f_raw, f_clean = files_of(ref)
-                Xb[i], Xa[i] = np.load(f_raw), np.load(f_clean)
+        if gate:
+            raw, clean, status, pcm = extract_features_batch([first[s] for s in gate], denoise=True, return_status=True,
+                                                             return_pcm=True)
+            raw, clean, status = raw.cpu().numpy(), clean.cpu().numpy(), status.cpu().numpy()
+            for i, stem in enumerate(gate):
+                wav, f_raw, f_clean = files_of(stem)
+                if status[len(gate) + i] & STATUS_CLEAN_FALLBACK:
+                    logging.error(f"clean_audio fail {stem}: Input must be finite")
+                else:
+                    jobs.append(pool.submit(wavio.write_wav_pcm16, wav, pcm[i].cpu().numpy(), TARGET_SR))
+                if overwrite or not os.path.exists(f_raw):
+                    vec_raw[stem] = raw[i]
+                    jobs.append(pool.submit(np.save, f_raw, raw[i]))
+                if overwrite or not os.path.exists(f_clean):
+                    vec_clean[stem] = clean[i]
+                    jobs.append(pool.submit(np.save, f_clean, clean[i]))
+        if raw_only:
+            raw = extract_features_batch([first[s] for s in raw_only]).cpu().numpy()
+            for i, stem in enumerate(raw_only):
+                vec_raw[stem] = raw[i]
+                jobs.append(pool.submit(np.save, files_of(stem)[1], raw[i]))
+        if from_wav:                                   # the clean vector of an existing WAV is the feature vector OF THAT WAV
+            pcms = [wavio.read_wav_pcm16(files_of(s)[0])[0] for s in from_wav]
+            cl = extract_features_batch(pcms).cpu().numpy()
+            for i, stem in enumerate(from_wav):
+                vec_clean[stem] = cl[i]
+                jobs.append(pool.submit(np.save, files_of(stem)[2], cl[i]))
+        for i, stem in enumerate(stems):
+            _, f_raw, f_clean = files_of(stem)
+            Xb[i] = vec_raw[stem] if stem in vec_raw else np.load(f_raw, allow_pickle=False)
+            Xa[i] = vec_clean[stem] if stem in vec_clean else np.load(f_clean, allow_pickle=False)
         for j in jobs:
             j.result()
     return Xb, Xa, kept

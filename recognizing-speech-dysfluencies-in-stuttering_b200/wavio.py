@@ -1,9 +1,8 @@
 """Minimal RIFF/WAVE PCM-16 mono I/O for the cache artefacts.
 
 The reference reads audio with librosa.load (pipeline1.py:100-106) and writes the cleaned
-clip with soundfile as WAV/PCM_16 (pipeline1.py:142).  Decoding compressed formats and
-resampling are upstream of this package: only 16 kHz mono PCM-16 WAV
-is handled here, which is exactly what the reference's clear_audio/ directory holds.
+clip with soundfile as WAV/PCM_16 (pipeline1.py:142).  Mono PCM-16 WAV is what the reference's
+clear_audio/ directory holds; MP3 inputs go through mp3io.py, other rates through the GPU resampler.
 """
 from __future__ import annotations
 
@@ -14,6 +13,12 @@ import numpy as np
 
 def read_wav(path: str):
     """-> (float32[n] in [-1, 1), sr).  int16 / 32768 like librosa.load on a PCM-16 file."""
+    pcm, sr = read_wav_pcm16(path)
+    return (pcm.astype(np.float32) / np.float32(32768.0)), sr
+
+
+def read_wav_pcm16(path: str):
+    """-> (int16[n], sr): the samples as stored (the PCM-16 entry points of the library take them as they are)."""
     with open(path, "rb") as fh:
         blob = fh.read()
     if len(blob) < 12 or blob[0:4] != b"RIFF" or blob[8:12] != b"WAVE":
@@ -31,8 +36,7 @@ def read_wav(path: str):
     codec, channels, sr, _, _, bits = fmt
     if codec != 1 or bits != 16 or channels != 1:
         raise ValueError(f"{path}: only mono PCM-16 is supported (codec={codec}, channels={channels}, bits={bits})")
-    pcm = np.frombuffer(data[:len(data) & ~1], dtype="<i2")
-    return (pcm.astype(np.float32) / np.float32(32768.0)), int(sr)
+    return np.frombuffer(data[:len(data) & ~1], dtype="<i2").astype(np.int16), int(sr)
 
 
 def write_wav_pcm16(path: str, pcm: np.ndarray, sr: int = 16000) -> None:

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(pkg):
     for name in declared:
         assert hasattr(lib, name), name
     loaded = pkg._lib.load()
-    assert loaded.dys_version() == 100
+    assert loaded.dys_version() == 200
     assert loaded.dys_last_error() == b""
 
 

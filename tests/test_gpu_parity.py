@@ -551,8 +551,12 @@ def test_batches_larger_than_the_workspace_limit_run_in_pieces(fe, synth, torch_
     """A batch whose per-clip workspace would not fit is run as consecutive pieces: same rows, status and PCM."""
     clips = [synth.synth_clip(200 + i, 30000 + 977 * i) for i in range(9)] + [synth.synth_clip(3, 4000)]
     a = fe.extract_features_batch(clips, denoise=True, return_status=True, return_pcm=True)
+    torch_cuda.cuda.synchronize()
+    fe.release_workspaces()                                       # the cached arena must not hide the limit
     monkeypatch.setenv("DYS_MAX_WORKSPACE_MB", "12")              # three or four clips per piece
+    calls0 = fe.abi_calls["features"]
     b = fe.extract_features_batch(clips, denoise=True, return_status=True, return_pcm=True)
+    assert fe.abi_calls["features"] - calls0 >= 2                 # the piece loop really ran (ADVICE r01)
     assert torch_cuda.equal(a[0], b[0]) and torch_cuda.equal(a[1], b[1]) and torch_cuda.equal(a[2], b[2])
     assert all(torch_cuda.equal(x, y) for x, y in zip(a[3], b[3]))
     r = fe.extract_features_batch(clips, denoise=False, return_status=True)
