@@ -426,6 +426,112 @@ def extract_features_host(audio: torch.Tensor, denoise: bool = True, prop_decrea
     return (out_raw, out_clean) if denoise else out_raw
 
 
+class PackedClips:
+    """Ragged host clips packed once into ONE pinned buffer, in length-sorted order (clips of similar length share
+    launch groups and waves of CTAs), ready to be streamed to the GPU chunk by chunk.  ``order[j]`` is the caller's index
+    of the j-th packed clip."""
+
+    def __init__(self, clips: Sequence, pcm16: bool | None = None, sort: bool = True):
+        lens = np.asarray([0 if c is None else int(np.asarray(c).shape[0]) for c in clips], dtype=np.int64)
+        self.order = np.argsort(lens, kind="stable") if sort else np.arange(len(clips))
+        self.pcm16 = _all_int16(clips) if pcm16 is None else bool(pcm16)
+        ordered = [clips[i] for i in self.order]
+        self.buf, self.starts, self.lengths, self.max_len = _pack_host(ordered, pcm16=self.pcm16)
+        self.n_clips = len(clips)
+
+    @property
+    def total_samples(self) -> int:
+        return int(self.lengths.astype(np.int64).sum())
+
+
+def extract_features_host_packed(packed: PackedClips, denoise: bool = True, prop_decrease: float | None = None,
+                                 chunk_samples: int = 400 * 48000, out_raw: torch.Tensor | None = None,
+                                 out_clean: torch.Tensor | None = None, device=None, compute_streams: int = 3):
+    """End-to-end host path for RAGGED clips (the real corpus: 0.45 - 10.1 s): the packed pinned buffer is pushed to the
+    device back to back in chunks of about ``chunk_samples`` samples cut at clip boundaries; compute streams take the
+    chunks in turn (one C-ABI call each over that chunk's clip range -- clips are addressed by starts + lengths, so the
+    device copy keeps the host layout) and send the rows back.  Returns host float32 [B,149] raw (and clean) in the
+    CALLER's clip order."""
+    prop = PROP_DECREASE if prop_decrease is None else float(prop_decrease)
+    dev = _device(device)
+    B = packed.n_clips
+    if out_raw is None:
+        out_raw = torch.empty((B, FEATURE_LEN), dtype=torch.float32).pin_memory()
+    if denoise and out_clean is None:
+        out_clean = torch.empty((B, FEATURE_LEN), dtype=torch.float32).pin_memory()
+    if B == 0:
+        return (out_raw, out_clean) if denoise else out_raw
+    esz = 2 if packed.pcm16 else 4
+    ends = packed.starts + ((packed.lengths.astype(np.int64) + 3) & ~3)          # padded extent of every clip in the buffer
+    cuts, c0 = [], 0                                                              # (first clip, end clip, first sample, end sample)
+    while c0 < B:
+        limit = packed.starts[c0] + max(int(chunk_samples), int(ends[c0] - packed.starts[c0]))
+        c1 = int(np.searchsorted(ends, limit, side="right"))
+        c1 = max(c1, c0 + 1)
+        cuts.append((c0, c1, int(packed.starts[c0]), int(ends[c1 - 1])))
+        c0 = c1
+    lib = _lib.load()
+    flag = 1 if denoise else 0
+    n_comp = max(1, min(int(compute_streams), 4))
+    srt_raw = torch.empty((B, FEATURE_LEN), dtype=torch.float32).pin_memory()     # rows in packed (sorted) order
+    srt_clean = torch.empty((B, FEATURE_LEN), dtype=torch.float32).pin_memory() if denoise else None
+    with torch.cuda.device(dev), _host_lock:
+        _lib.check(lib.dys_init(), "dys_init")
+        cur = torch.cuda.current_stream(dev)
+        streams = _host_streams(dev, 1 + n_comp)
+        copy_s, comp = streams[0], streams[1:]
+        total = int(ends[-1])
+        staging = _arena.get(dev, max(total * esz, 256), slot=11)[:total * esz].view(packed.buf.dtype)
+        d_starts = torch.from_numpy(packed.starts).to(dev)
+        d_lens = torch.from_numpy(np.ascontiguousarray(packed.lengths)).to(dev)
+        biggest = max(c1 - c0 for c0, c1, _, _ in cuts)
+        need = max(int(lib.dys_workspace_bytes(c1 - c0, int(packed.lengths[c0:c1].max()), flag)) for c0, c1, _, _ in cuts)
+        slots = []
+        for k in range(n_comp):
+            ws = _arena.get(dev, max(need, 256), slot=31 + k)
+            rows = _arena.get(dev, biggest * (2 * FEATURE_LEN * 4 + 8), slot=41 + k)
+            raw_k = rows[:biggest * FEATURE_LEN * 4].view(torch.float32).view(biggest, FEATURE_LEN)
+            clean_k = rows[biggest * FEATURE_LEN * 4:2 * biggest * FEATURE_LEN * 4].view(torch.float32).view(biggest, FEATURE_LEN)
+            st_k = rows[2 * biggest * FEATURE_LEN * 4:].view(torch.int32)
+            slots.append((ws, raw_k, clean_k, st_k))
+        for s_ in streams:
+            s_.wait_stream(cur)
+        landed = []
+        with torch.cuda.stream(copy_s):
+            for _, _, s0, s1 in cuts:
+                staging[s0:s1].copy_(packed.buf[s0:s1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_s)
+                landed.append(ev)
+        f_both = lib.dys_features_raw_clean_pcm16 if packed.pcm16 else lib.dys_features_raw_clean
+        f_raw = lib.dys_features_raw_pcm16 if packed.pcm16 else lib.dys_features_raw
+        in_ptr, st_ptr, ln_ptr = staging.data_ptr(), d_starts.data_ptr(), d_lens.data_ptr()
+        for i, ((c0, c1, _, _), ev) in enumerate(zip(cuts, landed)):
+            s_ = comp[i % n_comp]
+            ws, raw_k, clean_k, st_k = slots[i % n_comp]
+            cnt, mx = c1 - c0, int(packed.lengths[c0:c1].max())
+            with torch.cuda.stream(s_):
+                s_.wait_event(ev)
+                if denoise:
+                    rc = f_both(in_ptr, st_ptr + 8 * c0, ln_ptr + 4 * c0, cnt, mx, prop, raw_k.data_ptr(), clean_k.data_ptr(),
+                                st_k.data_ptr(), None, None, ws.data_ptr(), need, s_.cuda_stream)
+                else:
+                    rc = f_raw(in_ptr, st_ptr + 8 * c0, ln_ptr + 4 * c0, cnt, mx, raw_k.data_ptr(), st_k.data_ptr(),
+                               ws.data_ptr(), need, s_.cuda_stream)
+                _lib.check(rc, "dys_features_raw_clean" if denoise else "dys_features_raw")
+                srt_raw[c0:c1].copy_(raw_k[:cnt], non_blocking=True)
+                if denoise:
+                    srt_clean[c0:c1].copy_(clean_k[:cnt], non_blocking=True)
+        for s_ in comp:
+            cur.wait_stream(s_)
+        cur.synchronize()
+    idx = torch.from_numpy(packed.order)
+    out_raw[idx] = srt_raw                                                        # back to the caller's order (host, 149 floats per clip)
+    if denoise:
+        out_clean[idx] = srt_clean
+    return (out_raw, out_clean) if denoise else out_raw
+
+
 def extract_features_longform(recording, win: int = 48000, hop: int = 24000, denoise: bool = True,
                               prop_decrease: float | None = None, rank: int = 0, world: int = 1, device=None):
     """Long-form recordings (BASELINE config 4): sliding windows of ``win`` samples every ``hop`` samples, each an

@@ -272,3 +272,22 @@ def test_two_d_lengths_are_validated(fe, synth, torch_cuda):
         fe.extract_features_batch(X, lengths=[-1, 100])
     r = fe.extract_features_batch(X, lengths=[48000, 20000])
     np.testing.assert_array_equal(r[1].cpu().numpy(), fe.extract_features_batch([X[1, :20000].cpu().numpy()])[0].cpu().numpy())
+
+
+def test_ragged_host_streaming_equals_device_path(fe, synth, torch_cuda):
+    """VERDICT r01 next #9: packed ragged clips streamed chunk by chunk from pinned host memory == one device batch."""
+    torch = torch_cuda
+    rng = np.random.default_rng(3)
+    lens = np.clip((rng.lognormal(np.log(2.0), 0.6, 120) * 16000).astype(int), 3000, 150000)
+    base = synth.synth_clip(2, 150000)
+    clips = [np.ascontiguousarray(base[:n] * np.float32(0.4 + 0.004 * i)) for i, n in enumerate(lens)]
+    ref_raw, ref_clean = fe.extract_features_batch(clips, denoise=True)
+    for pcm in (False, True):
+        src = [owav.quantize_pcm16(c) for c in clips] if pcm else clips
+        if pcm:
+            ref_raw, ref_clean = fe.extract_features_batch(src, denoise=True)
+        packed = fe.PackedClips(src)
+        assert packed.pcm16 == pcm and np.all(np.diff(packed.lengths) >= 0)
+        h_raw, h_clean = fe.extract_features_host_packed(packed, denoise=True, chunk_samples=600000)
+        assert torch.equal(h_raw, ref_raw.cpu()) and torch.equal(h_clean, ref_clean.cpu())
+        assert torch.equal(fe.extract_features_host_packed(packed, denoise=False, chunk_samples=10 ** 9), ref_raw.cpu())
