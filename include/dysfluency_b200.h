@@ -64,6 +64,12 @@ DYS_API int dys_init(void);
 DYS_API int64_t dys_workspace_bytes(int32_t n_clips, int32_t max_len, int32_t with_clean);
 DYS_API int64_t dys_workspace_min_bytes(int32_t n_clips, int32_t max_len, int32_t with_clean);
 
+/* on != 0: dys_features_raw_clean* run the spectral gate and the clean branch on a library-owned high-priority side
+ * stream (forked from and joined to the caller's stream with events) while the raw clip's feature pass stays on the
+ * caller's stream; dys_workspace_bytes() then includes the raw branch's own scratch region.  Measured slower than the
+ * single-stream order on B200, so the default is off. */
+DYS_API int dys_set_overlap(int32_t on);
+
 /* extract_features(y, sr, "") for a batch                    [pipeline1.py:257-265, 206-239]
  *   d_audio   float32 samples; clip c = d_audio[d_starts[c] .. d_starts[c] + d_lengths[c])
  *             (clips may overlap -> sliding windows cost no copy; even d_starts enable 8-byte loads)

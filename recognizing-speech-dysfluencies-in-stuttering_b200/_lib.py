@@ -25,6 +25,7 @@ _SIGNATURES = {
     "dys_version": (C.c_int, []),
     "dys_last_error": (C.c_char_p, []),
     "dys_init": (C.c_int, []),
+    "dys_set_overlap": (C.c_int, [_i32]),
     "dys_workspace_bytes": (_i64, [_i32, _i32, _i32]),
     "dys_workspace_min_bytes": (_i64, [_i32, _i32, _i32]),
     "dys_features_raw": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp, _i64, _vp]),

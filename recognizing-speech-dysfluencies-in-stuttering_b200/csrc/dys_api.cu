@@ -1,8 +1,11 @@
 // C ABI of libdysb200.so (declared in include/dysfluency_b200.h): argument checks, workspace
 // carving, sub-batch loops.  No host copies, no CPU fallback.
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 
 #include "../../include/dysfluency_b200.h"
@@ -77,20 +80,63 @@ int check_common(const void* d_audio, const void* d_starts, const void* d_length
     return DYS_OK;
 }
 
-int run_features(const DeviceTables& tb, const ClipView& cv, int n_inst_total, const Layout& L, unsigned char* ws,
-                 size_t ws_bytes, float* out_raw, float* out_clean, int32_t* status, cudaStream_t stream) {
-    const size_t avail = ws_bytes - L.scratch_off;
-    const size_t per = feat_scratch_bytes(1, L.t_max);
-    int n_sub = int(std::min<size_t>(avail / per, size_t(sub_count(per, feat_cap(), n_inst_total))));
+// Feature pipeline over instances [inst_begin, inst_end) with `avail` bytes of scratch at `scratch`.
+int run_features(const DeviceTables& tb, const ClipView& cv, int inst_begin, int inst_end, int t_max, unsigned char* scratch,
+                 size_t avail, int cap, float* out_raw, float* out_clean, int32_t* status, cudaStream_t stream) {
+    const int n_inst_total = inst_end - inst_begin;
+    if (n_inst_total <= 0) return DYS_OK;
+    const size_t per = feat_scratch_bytes(1, t_max);
+    int n_sub = int(std::min<size_t>(avail / per, size_t(sub_count(per, cap, n_inst_total))));
     if (n_sub < 1) { set_error("workspace too small for one clip"); return DYS_ERR_WORKSPACE; }
-    while (n_sub > 1 && feat_scratch_bytes(n_sub, L.t_max) > avail) --n_sub;
+    while (n_sub > 1 && feat_scratch_bytes(n_sub, t_max) > avail) --n_sub;
     FeatScratch sc;
-    feat_scratch_carve(ws + L.scratch_off, n_sub, L.t_max, &sc);
-    for (int i0 = 0; i0 < n_inst_total; i0 += n_sub) {
-        const int cnt = std::min(n_sub, n_inst_total - i0);
+    feat_scratch_carve(scratch, n_sub, t_max, &sc);
+    for (int i0 = inst_begin; i0 < inst_end; i0 += n_sub) {
+        const int cnt = std::min(n_sub, inst_end - i0);
         DYS_CUDA_OK(launch_features(tb, cv, i0, cnt, sc, out_raw, out_clean, status, stream));
     }
     return DYS_OK;
+}
+
+// ---- two branches on two streams ---------------------------------------------------------------------------------
+// The raw clip's feature pass does not depend on the spectral gate.  The gate and the clean branch run on a
+// library-owned HIGH-priority side stream (one per caller stream and device, forked and joined with events), the raw
+// branch stays on the caller's stream: its CTAs are scheduled only where the gate leaves an SM idle -- the
+// latency-bound time-smoothing sweep (32-thread CTAs, little shared memory) and the tail of every wave.  The raw branch
+// needs its own scratch region, so this is used when the caller's workspace has dys_workspace_bytes(); smaller
+// workspaces run everything on the caller's stream.
+// MEASURED (B200, 10 000 3-s clips, round 2): 31.9 ms per step with the fork against 31.2 ms without (raw branch forked
+// at entry on an equal-priority stream: 31.6 against 31.0); the host streaming path loses 1 - 3 ms.  The co-running
+// kernels take bandwidth and shared memory from the gate's FFT kernels, which costs more than the idle time they fill.
+// It is therefore OFF by default; dys_set_overlap(1) enables it.
+std::atomic<int> g_overlap{0};
+int side_cap() { return env_int("DYS_SIDE_SUBBATCH", 4096); }
+size_t side_scratch_bytes(int n_clips, int t_max) {
+    return feat_scratch_bytes(sub_count(feat_scratch_bytes(1, t_max), side_cap(), std::max(n_clips, 1)), t_max);
+}
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+std::mutex g_side_mu;
+std::map<std::pair<int, cudaStream_t>, SideStream> g_side;
+bool side_stream_for(cudaStream_t caller, SideStream* out) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    std::lock_guard<std::mutex> lock(g_side_mu);
+    auto key = std::make_pair(dev, caller);
+    auto it = g_side.find(key);
+    if (it == g_side.end()) {
+        SideStream s;
+        int least = 0, greatest = 0;
+        cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        if (cudaStreamCreateWithPriority(&s.stream, cudaStreamNonBlocking, greatest) != cudaSuccess) return false;
+        if (cudaEventCreateWithFlags(&s.fork, cudaEventDisableTiming) != cudaSuccess) return false;
+        if (cudaEventCreateWithFlags(&s.join, cudaEventDisableTiming) != cudaSuccess) return false;
+        it = g_side.emplace(key, s).first;
+    }
+    *out = it->second;
+    return true;
 }
 
 }  // namespace
@@ -121,8 +167,14 @@ DYS_API int64_t dys_workspace_bytes(int32_t n_clips, int32_t max_len, int32_t wi
     if (with_clean) {
         const int n_items = sub_count(nr_scratch_bytes(1, L.ta_max), nr_cap(), int64_t(n_clips) * L.cpc);
         scratch = std::max(scratch, nr_scratch_bytes(n_items, L.ta_max));
+        if (g_overlap.load()) scratch += side_scratch_bytes(n_clips, L.t_max);   // the raw branch's own region (two-stream mode)
     }
     return int64_t(L.scratch_off + scratch);
+}
+
+DYS_API int dys_set_overlap(int32_t on) {
+    g_overlap.store(on != 0 ? 1 : 0);
+    return DYS_OK;
 }
 
 DYS_API int64_t dys_workspace_min_bytes(int32_t n_clips, int32_t max_len, int32_t with_clean) {
@@ -198,8 +250,9 @@ int features_raw_impl(const float* d_audio, const int16_t* d_pcm, const int64_t*
     }
     ClipView cv{};
     cv.audio = d_audio; cv.audio_q = d_pcm; cv.starts = d_starts; cv.lengths = d_lengths; cv.n_clips = n_clips; cv.max_len = max_len;
-    return run_features(*tb, cv, n_clips, L, static_cast<unsigned char*>(d_workspace), size_t(workspace_bytes), d_out,
-                        nullptr, d_status, static_cast<cudaStream_t>(stream));
+    return run_features(*tb, cv, 0, n_clips, L.t_max, static_cast<unsigned char*>(d_workspace) + L.scratch_off,
+                        size_t(workspace_bytes) - L.scratch_off, feat_cap(), d_out, nullptr, d_status,
+                        static_cast<cudaStream_t>(stream));
 }
 
 int features_raw_clean_impl(const float* d_audio, const int16_t* d_pcm, const int64_t* d_starts, const int32_t* d_lengths,
@@ -231,10 +284,29 @@ int features_raw_clean_impl(const float* d_audio, const int16_t* d_pcm, const in
     cv.audio = d_audio; cv.audio_q = d_pcm; cv.starts = d_starts; cv.lengths = d_lengths; cv.n_clips = n_clips; cv.max_len = max_len;
     cv.clean = clean; cv.clean_pitch = L.clean_pitch; cv.clean_peak = peak; cv.clean_flag = flag; cv.clean_q = clean_q;
 
+    // ---- fork: the gate and the clean branch go to the library's high-priority side stream, the raw branch stays on the
+    // caller's stream (streams created by the caller have the lowest priority: its CTAs only fill what the gate leaves idle)
+    const size_t side_bytes = side_scratch_bytes(n_clips, L.t_max);
+    const bool overlap = g_overlap.load() != 0 && workspace_bytes >= dys_workspace_bytes(n_clips, max_len, 1);
+    const size_t main_bytes = size_t(workspace_bytes) - (overlap ? side_bytes : 0);     // [0, main_bytes): everything but the raw branch's region
+    SideStream side;
+    struct Joiner {
+        cudaStream_t stream = nullptr, from = nullptr;
+        cudaEvent_t event = nullptr;
+        ~Joiner() { if (event && cudaEventRecord(event, from) == cudaSuccess) cudaStreamWaitEvent(stream, event, 0); }
+    } joiner;                                                              // the caller's stream waits for the side stream on every return path
+    const bool forked = overlap && side_stream_for(st, &side);
+    cudaStream_t gate_st = st;
+    if (forked) {
+        DYS_CUDA_OK(cudaEventRecord(side.fork, st));                       // inputs (and earlier users of the workspace) are ready here
+        DYS_CUDA_OK(cudaStreamWaitEvent(side.stream, side.fork, 0));
+        gate_st = side.stream;
+        joiner.stream = st; joiner.from = side.stream; joiner.event = side.join;
+    }
     // ---- spectral gate over sub-batches of chunks ------------------------------------------
-    DYS_CUDA_OK(launch_clean_init(cv, peak, flag, st));
+    DYS_CUDA_OK(launch_clean_init(cv, peak, flag, gate_st));
     {
-        const size_t avail = size_t(workspace_bytes) - L.scratch_off;
+        const size_t avail = main_bytes - L.scratch_off;
         const size_t per = nr_scratch_bytes(1, L.ta_max);
         const int64_t n_items = int64_t(n_clips) * L.cpc;
         int n_sub = int(std::min<size_t>(avail / per, size_t(sub_count(per, nr_cap(), n_items))));
@@ -244,12 +316,17 @@ int features_raw_clean_impl(const float* d_audio, const int16_t* d_pcm, const in
         nr_scratch_carve(ws + L.scratch_off, n_sub, L.ta_max, &sc);
         for (int64_t i0 = 0; i0 < n_items; i0 += n_sub) {
             const int cnt = int(std::min<int64_t>(n_sub, n_items - i0));
-            DYS_CUDA_OK(launch_denoise(*tb, cv, clean, peak, flag, L.cpc, int(i0), cnt, sc, prop_decrease, st));
+            DYS_CUDA_OK(launch_denoise(*tb, cv, clean, peak, flag, L.cpc, int(i0), cnt, sc, prop_decrease, gate_st));
+            if (forked && i0 == 0) {                                       // the raw branch is queued behind the first gate launches
+                if (int rc = run_features(*tb, cv, 0, n_clips, L.t_max, ws + main_bytes, side_bytes, side_cap(), d_out_raw,
+                                          d_out_clean, d_status, st)) return rc;
+            }
         }
     }
-    DYS_CUDA_OK(launch_quantize_pcm(cv, clean_q, d_clean_pcm, d_pcm_starts, st));
-    // ---- features of both branches ----------------------------------------------------------
-    return run_features(*tb, cv, 2 * n_clips, L, ws, size_t(workspace_bytes), d_out_raw, d_out_clean, d_status, st);
+    DYS_CUDA_OK(launch_quantize_pcm(cv, clean_q, d_clean_pcm, d_pcm_starts, gate_st));
+    // ---- features: the clean branch (and the raw one when it was not forked) -----------------------------------
+    return run_features(*tb, cv, forked ? n_clips : 0, 2 * n_clips, L.t_max, ws + L.scratch_off, main_bytes - L.scratch_off,
+                        feat_cap(), d_out_raw, d_out_clean, d_status, gate_st);
 }
 
 }}  // namespace dys::(anonymous)
