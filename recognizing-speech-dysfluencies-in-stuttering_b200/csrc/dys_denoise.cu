@@ -48,6 +48,9 @@ constexpr int kThreads = kWarps * 32;
 // latency is set by how many SMs its frames spread over.
 constexpr int kBigGroup = 592;
 constexpr int kFramesPerCtaSmall = 64, kFramesPerCtaBig = 192;
+constexpr int kIirSegShift = 6;
+constexpr int kIirSeg = 1 << kIirSegShift;           // frames per forward-IIR interval = check-point spacing of the backward sweep
+static_assert(kFramesPerCtaSmall % kIirSeg == 0 && kFramesPerCtaBig % kIirSeg == 0, "CTAs must own whole intervals");
 
 struct NrGeom {
     int clip, n, c0, out_len, L, Tn, t_first, t_last;
@@ -136,12 +139,13 @@ __device__ __forceinline__ double2 split_factor(const LaneTrig& t) {
     return make_double2(fma(t.ck, cq, -(t.sk * sq)), fma(t.sk, cq, t.ck * sq));
 }
 
-// Windowed frame t of the zero-padded chunk -> STFT bins.  On return x[q] = D[lane + 32 q] (q < 16)
-// and *nyq = D[512] (real).
-template <bool kPcm>
+// Windowed frame t of the zero-padded chunk -> STFT bins.  sink(q, D[lane + 32 q]) is called for q = 0..15 as each bin
+// leaves the real-FFT split (no second register array: the accumulators of the caller stay in registers), then
+// *nyq = D[512] (real).
+template <bool kPcm, typename Sink>
 __device__ __forceinline__ void nr_frame_stft(const NrTables& sm, const NrFwdTables& fw, double2* xbuf,
                                               const float* __restrict__ base, const int16_t* __restrict__ base_q, bool vec_ok,
-                                              const NrGeom& g, int t, int lane, double2 (&x)[16], double* nyq) {
+                                              const NrGeom& g, int t, int lane, Sink&& sink, double* nyq) {
     double2 v[16];
     const int p0 = t * kNrHop - kNrFft / 2;                 // padded-chunk coordinate of the frame's first sample
     static_for<16>([&](auto im) {
@@ -185,7 +189,7 @@ __device__ __forceinline__ void nr_frame_stft(const NrTables& sm, const NrFwdTab
         const double2 p = lds_once(&xbuf[512 - k]);
         const double ex = z.x + p.x, ey = z.y - p.y, dx = z.x - p.x, dy = z.y + p.y;
         const double2 cs = lds_once(&fw.split[k]);
-        x[q] = make_double2(0.5 * (ex + (cs.x * dy - cs.y * dx)), 0.5 * (ey - (cs.x * dx + cs.y * dy)));
+        sink(iq, make_double2(0.5 * (ex + (cs.x * dy - cs.y * dx)), 0.5 * (ey - (cs.x * dx + cs.y * dy))));
     });
     const double2 z0 = xbuf[512];
     *nyq = z0.x - z0.y;
@@ -219,43 +223,77 @@ k_nr_stft_mag(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
                         (g.c0 & 1) == 0;
     double* mag = sc.mag + size_t(li) * sc.ta_max * kNrBinsPad;
     double2* spec = sc.spec + size_t(li) * sc.ta_max * kNrBinsPad;
-    for (int t = t_begin + warp; t < t_end; t += kWarps) {
-        {   // this warp's next frame starts 2048 samples further on: pull its 32 lines towards L2 while this one is transformed
-            const long long s_next = (long long)(t + kWarps) * kNrHop - kNrFft / 2 - kNrPad + g.c0 + 32 * lane;
-            if (t + kWarps < t_end && s_next >= 0 && s_next < g.n) {
-                if constexpr (kPcm) { if ((lane & 1) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(base_q + s_next)); }
-                else asm volatile("prefetch.global.L2 [%0];" ::"l"(base + s_next));
+    // Forward half of filtfilt([b], [1, b - 1]) -- f[t] = b A[t] + r f[t-1], r = 1 - b -- without a sweep of its own: the
+    // recursion is linear, so over an interval of kIirSeg frames  f[end] = r^len f[start - 1] + sum_u b A[u] r^(len-1-u).
+    // Each warp keeps the Horner sum over ITS frames of the interval (every 8th: acc <- r^8 acc + b |D|) while the
+    // magnitudes are still in registers; at the interval's end the 8 sums are weighted (r^0..r^7), added in warp order
+    // through the FFT tiles and stored: 4 KB per 64 frames instead of re-reading the 0.27 MB of |D| they cover.
+    // k_nr_iir_mask chains the intervals (check-points of its backward sweep).
+    const double iir_b = tb.iir_b, iir_r = 1.0 - iir_b;
+    double r8 = iir_r * iir_r; r8 *= r8; r8 *= r8;
+    double* part = sc.part + size_t(li) * sc.n_seg_max * kNrBinsPad;
+    for (int t0 = t_begin; t0 < t_end; t0 += kIirSeg) {
+        const int seg_len = min(kIirSeg, t_end - t0);
+        double acc[16], acc_nyq = 0.0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) acc[q] = 0.0;
+        int last_u = -1;
+        for (int u = warp; u < seg_len; u += kWarps) {
+            const int t = t0 + u;
+            last_u = u;
+            {   // this warp's next frame starts 2048 samples further on: pull its 32 lines towards L2 while this one is transformed
+                const long long s_next = (long long)(t + kWarps) * kNrHop - kNrFft / 2 - kNrPad + g.c0 + 32 * lane;
+                if (t + kWarps < t_end && s_next >= 0 && s_next < g.n) {
+                    if constexpr (kPcm) { if ((lane & 1) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(base_q + s_next)); }
+                    else asm volatile("prefetch.global.L2 [%0];" ::"l"(base + s_next));
+                }
             }
+            double* row = mag + size_t(t - g.t_first) * kNrBinsPad;
+            double2* srow = spec + size_t(t - g.t_first) * kNrBinsPad;
+            double nyq;
+            nr_frame_stft<kPcm>(sm.tab, sm.fwd, sm.xbuf[warp], base, base_q, vec_ok, g, t, lane,
+                                [&](auto iq, const double2 xq) {
+                                    constexpr int q = decltype(iq)::value;
+                                    srow[lane + 32 * q] = xq;
+                                    const double m = sqrt(xq.x * xq.x + xq.y * xq.y);
+                                    row[lane + 32 * q] = m;
+                                    acc[q] = fma(r8, acc[q], iir_b * m);
+                                }, &nyq);
+            acc_nyq = fma(r8, acc_nyq, iir_b * fabs(nyq));
+            if (lane == 0) { srow[512] = make_double2(nyq, 0.0); row[512] = fabs(nyq); }
+            __syncwarp();
         }
-        double2 x[16];
-        double nyq;
-        nr_frame_stft<kPcm>(sm.tab, sm.fwd, sm.xbuf[warp], base, base_q, vec_ok, g, t, lane, x, &nyq);
-        double* row = mag + size_t(t - g.t_first) * kNrBinsPad;
-        double2* srow = spec + size_t(t - g.t_first) * kNrBinsPad;
+        // weight r^(seg_len - 1 - last_u) brings the warp's sum to the interval's last frame (0..7 steps; 0 frames: no share)
+        double w = 0.0;
+        if (last_u >= 0) { w = 1.0; for (int e = seg_len - 1 - last_u; e > 0; --e) w *= iir_r; }
+        double* pub = reinterpret_cast<double*>(sm.xbuf[warp]);
         static_for<16>([&](auto iq) {
             constexpr int q = decltype(iq)::value;
-            srow[lane + 32 * q] = x[q];
-            row[lane + 32 * q] = sqrt(x[q].x * x[q].x + x[q].y * x[q].y);
+            pub[lane + 32 * q] = acc[q] * w;
         });
-        if (lane == 0) { srow[512] = make_double2(nyq, 0.0); row[512] = fabs(nyq); }
-        __syncwarp();
+        if (lane == 0) pub[512] = acc_nyq * w;
+        __syncthreads();
+        double* prow = part + size_t((t0 - g.t_first) / kIirSeg) * kNrBinsPad;
+        for (int k = tid; k < kNrBins; k += kThreads) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w2 = 0; w2 < kWarps; ++w2) sum += reinterpret_cast<const double*>(sm.xbuf[w2])[k];
+            prow[k] = sum;
+        }
+        __syncthreads();
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // filtfilt([b], [1, b - 1]) over time + sigmoid + 7-tap time smoothing, one thread per bin.
 constexpr int kIirThreads = 32;
-#ifndef DYS_IIR_FWD
-#define DYS_IIR_FWD 8
-#endif
-constexpr int kIirFwd = DYS_IIR_FWD;                // rows per batch of the forward sweep (divides the check-point spacing)
-constexpr int kIirCkShift = 7;                       // forward state check-pointed every 128 frames
-static_assert((1 << kIirCkShift) % kIirFwd == 0, "check-point rows must fall on batch ends of the forward sweep");
-constexpr int kIirMaxCk = 24;                        // covers ta_max <= 3072 (a full 660 000-sample chunk has 2579)
+constexpr int kIirCkShift = kIirSegShift;            // forward state known at the end of every interval of k_nr_stft_mag
+constexpr int kIirMaxSeg = 48;                       // covers ta_max <= 3072 (a full 660 000-sample chunk has 2579)
 
 __global__ void __launch_bounds__(kIirThreads)
 k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrScratch sc, int32_t* __restrict__ clean_flag) {
-    __shared__ double ck[kIirMaxCk][kIirThreads];
+    extern __shared__ double ck_raw[];                // [n_seg_max][kIirThreads]: f at the last frame of every interval
+    double (*ck)[kIirThreads] = reinterpret_cast<double (*)[kIirThreads]>(ck_raw);
     const int li = blockIdx.x;
     const int k = blockIdx.y * kIirThreads + threadIdx.x;
     const NrGeom g = nr_geom(cv, item0 + li, cpc);
@@ -264,29 +302,25 @@ k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
     constexpr size_t P = kNrBinsPad;
     double* col = sc.mag + size_t(li) * sc.ta_max * P + k;
     const double b = tb.iir_b, r = 1.0 - b, rinv = 1.0 / r;
-    // forward: f[t] = b A[t] + (1 - b) f[t-1],  f[-1] := A[0]  (lfilter_zi steady state; A[0] = 0 when padded)
+    // forward: f[t] = b A[t] + (1 - b) f[t-1],  f[-1] := A[0]  (lfilter_zi steady state; A[0] = 0 when padded).
+    // k_nr_stft_mag left  sum_u b A[u] r^(len-1-u)  per interval: chain them,  f[end] = r^len f[start-1] + sum.
     double prev = (g.t_first == 0) ? col[0] : 0.0;
-    int i = 0;
-    {   // The sweep has two flops per row and waits on DRAM: batches of kIirFwd rows, the next batch's loads in flight while
-        // the serial recurrence runs over the current one, and the ragged tail fetched as one more (predicated) batch
-        // instead of row by row.  (The registers are free here: the backward sweep below needs more.)
-        double a[kIirFwd], an[kIirFwd];
-        auto load_batch = [&](double (&d)[kIirFwd], int i0) {
+    {
+        double rseg = r;                              // r^kIirSeg by squaring
 #pragma unroll
-            for (int u = 0; u < kIirFwd; ++u) d[u] = (i0 + u < Ta) ? col[size_t(i0 + u) * P] : 0.0;
-        };
-        load_batch(a, 0);
-        for (; i + kIirFwd <= Ta; i += kIirFwd) {
-            load_batch(an, i + kIirFwd);
-#pragma unroll
-            for (int u = 0; u < kIirFwd; ++u) prev = b * a[u] + r * prev;
-            if (((i + kIirFwd) & ((1 << kIirCkShift) - 1)) == 0) ck[((i + kIirFwd) >> kIirCkShift) - 1][threadIdx.x] = prev;
-#pragma unroll
-            for (int u = 0; u < kIirFwd; ++u) a[u] = an[u];
+        for (int e = 0; e < kIirSegShift; ++e) rseg *= rseg;
+        const double* part = sc.part + size_t(li) * sc.n_seg_max * P + k;
+        const int n_seg = (Ta + kIirSeg - 1) >> kIirSegShift;
+        double pnext = part[0];
+        for (int j = 0; j < n_seg; ++j) {
+            const double pj = pnext;
+            if (j + 1 < n_seg) pnext = part[size_t(j + 1) * P];
+            const int len = min(kIirSeg, Ta - (j << kIirSegShift));
+            double rl = rseg;
+            if (len < kIirSeg) { rl = 1.0; for (int e = 0; e < len; ++e) rl *= r; }
+            prev = fma(rl, prev, pj);
+            ck[j][threadIdx.x] = prev;
         }
-#pragma unroll
-        for (int u = 0; u < kIirFwd; ++u)                   // fewer than kIirFwd rows left: none of them is a check-point row
-            if (i + u < Ta) prev = b * a[u] + r * prev;
     }
     // frames t_last+1 .. Tn-1 hold zeros: f decays geometrically and the backward recursion over them,
     // started from S[Tn] := f[Tn-1], collapses to  S[t_last+1] = r F u,  u <- b + r^2 u  (m-1 times from 1).
@@ -697,17 +731,22 @@ int nr_ta_max(int max_len) {
     return 1 + (kNrChunk + 2 * kNrPad) / kNrHop;
 }
 
+static int nr_seg_max(int ta_max) { return (ta_max + kIirSeg - 1) / kIirSeg; }
+
 size_t nr_scratch_bytes(int n_items, int ta_max) {
     auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
-    return al(size_t(n_items) * ta_max * kNrBinsPad * 8) + al(size_t(n_items) * ta_max * kNrBinsPad * 16);
+    return al(size_t(n_items) * ta_max * kNrBinsPad * 8) + al(size_t(n_items) * ta_max * kNrBinsPad * 16) +
+           al(size_t(n_items) * nr_seg_max(ta_max) * kNrBinsPad * 8);
 }
 
 void nr_scratch_carve(void* base, int n_items, int ta_max, NrScratch* out) {
     auto al = [](size_t b) { return (b + 255) & ~size_t(255); };
     unsigned char* p = static_cast<unsigned char*>(base);
     out->mag = reinterpret_cast<double*>(p); p += al(size_t(n_items) * ta_max * kNrBinsPad * 8);
-    out->spec = reinterpret_cast<double2*>(p);
+    out->spec = reinterpret_cast<double2*>(p); p += al(size_t(n_items) * ta_max * kNrBinsPad * 16);
+    out->part = reinterpret_cast<double*>(p);
     out->ta_max = ta_max;
+    out->n_seg_max = nr_seg_max(ta_max);
 }
 
 cudaError_t launch_clean_init(const ClipView& cv, float* clean_peak, int32_t* clean_flag, cudaStream_t stream) {
@@ -723,7 +762,7 @@ cudaError_t launch_denoise(const DeviceTables& tb, const ClipView& cv, float* cl
     if (cudaError_t e = ensure_dynamic_smem<kK_nr_stft_mag>(k_nr_stft_mag<false>, int(sizeof(MagSmem)))) return e;
     if (cudaError_t e = ensure_dynamic_smem<kK_nr_stft_mag + 32>(k_nr_stft_mag<true>, int(sizeof(MagSmem)))) return e;
     if (cudaError_t e = ensure_dynamic_smem<kK_nr_apply_ola>(k_nr_apply_ola<kApplyWarps>, int(sizeof(ApplySmem<kApplyWarps>)))) return e;
-    if (sc.ta_max > kIirMaxCk << kIirCkShift) return cudaErrorInvalidValue;
+    if (sc.ta_max > kIirMaxSeg << kIirSegShift) return cudaErrorInvalidValue;
     const bool big = n_items >= kBigGroup;
     const int fpc = big ? kFramesPerCtaBig : kFramesPerCtaSmall;
     const int gy = (sc.ta_max + fpc - 1) / fpc;
@@ -733,8 +772,8 @@ cudaError_t launch_denoise(const DeviceTables& tb, const ClipView& cv, float* cl
       if (cv.audio_q) k_nr_stft_mag<true><<<dim3(n_items, gy), kThreads, sizeof(MagSmem), stream>>>(tb, cvw, cpc, item0, sc, fpc);
       else k_nr_stft_mag<false><<<dim3(n_items, gy), kThreads, sizeof(MagSmem), stream>>>(tb, cvw, cpc, item0, sc, fpc); }
     { LaunchScope ls(kK_nr_iir_mask, stream);
-      k_nr_iir_mask<<<dim3(n_items, (kNrBins + kIirThreads - 1) / kIirThreads), kIirThreads, 0, stream>>>(tb, cvw, cpc, item0, sc,
-                                                                                                      clean_flag); }
+      k_nr_iir_mask<<<dim3(n_items, (kNrBins + kIirThreads - 1) / kIirThreads), kIirThreads,
+                      size_t(sc.n_seg_max) * kIirThreads * sizeof(double), stream>>>(tb, cvw, cpc, item0, sc, clean_flag); }
     // output blocks of 256 samples per chunk, split evenly over CTAs of about 16 W frames
     const int max_out = std::min(cv.max_len, kNrChunk);
     const int n_blocks = (kNrPad + std::max(max_out, 1) - 1) / kNrHop - kNrPad / kNrHop + 1;

@@ -85,7 +85,9 @@ cudaError_t launch_qc(const DeviceTables& tb, const ClipView& cv, float* out, vo
 struct NrScratch {
     double* mag;       // [n_items][ta_max][kNrBinsPad]   |STFT|, then (in place) the time-smoothed sigmoid mask
     double2* spec;     // [n_items][ta_max][kNrBinsPad]   complex STFT (read back when the mask is applied)
+    double* part;      // [n_items][n_seg_max][kNrBinsPad] forward-IIR sums of every 64-frame interval (k_nr_stft_mag -> k_nr_iir_mask)
     int ta_max;
+    int n_seg_max;
 };
 size_t nr_scratch_bytes(int n_items, int ta_max);
 void nr_scratch_carve(void* base, int n_items, int ta_max, NrScratch* out);

@@ -104,11 +104,18 @@ def main():
     counts = np.bincount(pred, minlength=3).astype(np.float64)
     stats = torch.tensor([t_feat, t_gen, t_cmvn, t_rf, float(hi - lo)], dtype=torch.float64, device=dev)
     cls = torch.from_numpy(counts).to(dev)
+    # order-independent fingerprints of the BITS of every vector (and of the generated clips): the 1-GPU and the 8-GPU run of
+    # one commit must print the same numbers -- a clip's vectors depend on nothing but the clip
+    raw = torch.cat(raws)
+    sums = torch.stack([raw.view(torch.int32).to(torch.int64).sum(), clean.view(torch.int32).to(torch.int64).sum(),
+                        (raw.view(torch.int32).to(torch.int64) * 2654435761 % 1000003).sum(),
+                        (clean.view(torch.int32).to(torch.int64) * 2654435761 % 1000003).sum()])
     if world > 1:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         dist.all_reduce(stats[4:], op=dist.ReduceOp.SUM)
         dist.all_reduce(cls, op=dist.ReduceOp.SUM)
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
         stats[:4] = mx[:4]
     if rank == 0:
         t_feat, t_gen, t_cmvn, t_rf, total = stats.tolist()
@@ -118,6 +125,8 @@ def main():
                 "on_device_generation_s": t_gen, "global_cmvn_fit_and_apply_s": t_cmvn,
                 "classifier_predict_s_cpu": t_rf, "predicted_class_counts": cls.tolist(),
                 "scaler_mean_first3": scaler.mean_[:3].tolist(),
+                "feature_bits_fingerprint": {"raw_sum": int(sums[0]), "clean_sum": int(sums[1]), "raw_hash": int(sums[2]),
+                                             "clean_hash": int(sums[3])},
                 "note": "times are max over ranks; the classifier is the reference's scikit-learn RandomForest on the host"}
         out.write(json.dumps(line) + "\n")
         out.flush()
