@@ -43,11 +43,17 @@ def _worker(rank, world, port, out_dir):
         lo, hi = pkg.sharding.shard_range(g["X"].shape[0], rank, world)
         X = g["X"][lo:hi]
         sc = pkg.scaler
-        # pass 1: global mean; pass 2: moments about it (sklearn's corrected two-pass variance)
+        # the default schedule: ONE all-reduce of the moments about zero (GlobalScaler.fit) ...
         acc0 = sc.allreduce_moments(torch.from_numpy(_moments_about(X, 0.0)))
+        mean_1, var_1, scale_1, n_1 = sc.finalize_moments(acc0, None)
+        # ... and the two-pass one (GlobalScaler(two_pass=True)): global mean, then moments about it
         mean0 = (acc0[1:150] / acc0[0]).numpy()
         acc1 = sc.allreduce_moments(torch.from_numpy(_moments_about(X, mean0)))
         mean, var, scale, n = sc.finalize_moments(acc1, mean0)
+        np.testing.assert_allclose(mean_1, mean, rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(var_1, var, rtol=1e-11, atol=1e-13)
+        np.testing.assert_allclose(scale_1, scale, rtol=1e-11, atol=1e-13)
+        mean, var, scale, n = mean_1, var_1, scale_1, n_1        # the reference's pickle is compared with the one-pass result
         # every rank holds the same statistics afterwards
         gathered = [torch.zeros(149, dtype=torch.float64) for _ in range(world)]
         dist.all_gather(gathered, torch.from_numpy(mean))
