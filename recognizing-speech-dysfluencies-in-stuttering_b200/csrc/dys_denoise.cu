@@ -26,6 +26,10 @@
 #include <cfloat>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include <cuda.h>                 // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link)
 
 #include "dys_fft.cuh"
 #include "dys_kernels.h"
@@ -290,10 +294,53 @@ constexpr int kIirThreads = 32;
 constexpr int kIirCkShift = kIirSegShift;            // forward state known at the end of every interval of k_nr_stft_mag
 constexpr int kIirMaxSeg = 48;                       // covers ta_max <= 3072 (a full 660 000-sample chunk has 2579)
 
+// ---- bulk-tensor (TMA) ring for the backward sweep ------------------------------------------------------------------
+// The sweep walks |D| from the last frame to the first, 8 rows at a time.  With kTma the rows do not go through the
+// load/store unit and registers: lane 0 asks the copy engine for [8 rows x 32 bins] boxes of the [items x frames][520]
+// float64 matrix (cp.async.bulk.tensor.2d, one instruction per 2 KB tile), kIirStages tiles ahead, each landing in
+// shared memory and flipping an mbarrier; the warp waits on the barrier, takes its 8 values from the tile and hands
+// the stage back to the engine.  Bins past 519 (the last slab) are filled with zeros by the engine.
+constexpr int kIirRows = 8;                          // rows per tile = rows per straight-line batch
+#ifndef DYS_IIR_STAGES
+#define DYS_IIR_STAGES 4
+#endif
+constexpr int kIirStages = DYS_IIR_STAGES;
+constexpr int kIirTileBytes = kIirRows * kIirThreads * 8;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return unsigned(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, void* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <bool kTma>
 __global__ void __launch_bounds__(kIirThreads)
-k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrScratch sc, int32_t* __restrict__ clean_flag) {
-    extern __shared__ double ck_raw[];                // [n_seg_max][kIirThreads]: f at the last frame of every interval
-    double (*ck)[kIirThreads] = reinterpret_cast<double (*)[kIirThreads]>(ck_raw);
+k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrScratch sc, int32_t* __restrict__ clean_flag,
+              const __grid_constant__ CUtensorMap mag_map) {
+    extern __shared__ __align__(128) unsigned char iir_smem[];
+    // kTma: [kIirStages tiles of 8 x 32 doubles][kIirStages mbarriers], then in both cases
+    // ck[n_seg_max][kIirThreads]: f at the last frame of every interval
+    double* tiles = reinterpret_cast<double*>(iir_smem);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(iir_smem + (kTma ? kIirStages * kIirTileBytes : 0));
+    double (*ck)[kIirThreads] = reinterpret_cast<double (*)[kIirThreads]>(iir_smem + (kTma ? kIirStages * kIirTileBytes + 64 : 0));
     const int li = blockIdx.x;
     const int k = blockIdx.y * kIirThreads + threadIdx.x;
     const NrGeom g = nr_geom(cv, item0 + li, cpc);
@@ -386,7 +433,46 @@ k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
             emit(i_ + 3, m0);
         }
     }
-    if (i_ >= 7) {
+    if constexpr (kTma) {
+        if (i_ >= 7) {
+            const int lane = threadIdx.x;
+            const int n_batch = (i_ + 1) >> 3;                        // rows i_ .. 0 in batches of 8 (i_ + 1 is a multiple of 8)
+            const int col0 = blockIdx.y * kIirThreads;
+            const int row_base = li * sc.ta_max;                      // this chunk's first row in the [items x frames] matrix
+            if (lane == 0) {
+                for (int s_ = 0; s_ < kIirStages; ++s_) mbar_init(&bars[s_], 1);
+                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            }
+            __syncwarp();
+            if (lane == 0) {
+                for (int j = 0; j < min(kIirStages, n_batch); ++j) {
+                    mbar_expect_tx(&bars[j], kIirTileBytes);
+                    tma_load_2d(tiles + j * (kIirTileBytes / 8), &mag_map, col0, row_base + i_ - 7 - 8 * j, &bars[j]);
+                }
+            }
+            for (int j = 0; j < n_batch; ++j, i_ -= 8) {
+                const int st_ = j % kIirStages;
+                mbar_wait(&bars[st_], unsigned(j / kIirStages) & 1u);
+                const double* tile = tiles + st_ * (kIirTileBytes / 8) + lane;
+                double a[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a[u] = tile[(7 - u) * kIirThreads];        // a[u] = row i_ - u
+                __syncwarp();                                         // every lane holds its 8 values: the stage is free again
+                if (lane == 0 && j + kIirStages < n_batch) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // our reads before the engine's writes
+                    mbar_expect_tx(&bars[st_], kIirTileBytes);
+                    tma_load_2d(tiles + st_ * (kIirTileBytes / 8), &mag_map, col0, row_base + i_ - 7 - 8 * kIirStages, &bars[st_]);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const double m0 = gate(a[u]);
+                    if (u < 7) fcur = (fcur - b * a[u]) * rinv;
+                    else rewind(i_ - 7, a[7]);
+                    emit(i_ - u + 3, m0);
+                }
+            }
+        }
+    } else if (i_ >= 7) {
         double a[8], an[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) a[u] = col[size_t(i_ - u) * P];
@@ -756,6 +842,42 @@ cudaError_t launch_clean_init(const ClipView& cv, float* clean_peak, int32_t* cl
     return cudaGetLastError();
 }
 
+// [n_items x ta_max rows][520 columns] float64 view of the |D| scratch for cp.async.bulk.tensor; box = 8 rows x 32 bins.
+// The encoder lives in the driver: fetched once through the runtime, no link against libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+static bool iir_tma_enabled() {
+    // MEASURED (B200, 10 000 3-s clips, round 2): 4.09 - 4.15 ms per step with 2 - 4 stages against 3.97 ms for the
+    // register-pipelined loads (6 / 8 stages: 4.65 / 5.49 ms).  The sweep is bound by its dependent float64 chain (exp and
+    // two reciprocals per element) and wants as many resident warps as possible; the ring's shared memory costs
+    // residency (24 instead of 32 single-warp CTAs per SM) and the loads were already off the critical path.
+    // So the copy-engine path is opt-in: DYS_IIR_TMA=1.
+    static const bool on = [] { const char* v = std::getenv("DYS_IIR_TMA"); return v && v[0] == '1'; }();
+    return on;
+}
+static bool make_mag_map(const NrScratch& sc, int n_items, CUtensorMap* map) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {cuuint64_t(kNrBinsPad), cuuint64_t(n_items) * cuuint64_t(sc.ta_max)};
+    const cuuint64_t strides[1] = {cuuint64_t(kNrBinsPad) * 8};
+    const cuuint32_t box[2] = {cuuint32_t(kIirThreads), cuuint32_t(kIirRows)};
+    const cuuint32_t estr[2] = {1, 1};
+    if (dims[1] >= (cuuint64_t(1) << 31)) return false;
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, sc.mag, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 cudaError_t launch_denoise(const DeviceTables& tb, const ClipView& cv, float* clean, float* clean_peak, int32_t* clean_flag,
                            int cpc, int item0, int n_items, const NrScratch& sc, float prop_decrease, cudaStream_t stream) {
     if (n_items <= 0) return cudaSuccess;
@@ -771,9 +893,17 @@ cudaError_t launch_denoise(const DeviceTables& tb, const ClipView& cv, float* cl
     { LaunchScope ls(kK_nr_stft_mag, stream);
       if (cv.audio_q) k_nr_stft_mag<true><<<dim3(n_items, gy), kThreads, sizeof(MagSmem), stream>>>(tb, cvw, cpc, item0, sc, fpc);
       else k_nr_stft_mag<false><<<dim3(n_items, gy), kThreads, sizeof(MagSmem), stream>>>(tb, cvw, cpc, item0, sc, fpc); }
-    { LaunchScope ls(kK_nr_iir_mask, stream);
-      k_nr_iir_mask<<<dim3(n_items, (kNrBins + kIirThreads - 1) / kIirThreads), kIirThreads,
-                      size_t(sc.n_seg_max) * kIirThreads * sizeof(double), stream>>>(tb, cvw, cpc, item0, sc, clean_flag); }
+    {
+        const dim3 grid(n_items, (kNrBins + kIirThreads - 1) / kIirThreads);
+        const size_t ck_bytes = size_t(sc.n_seg_max) * kIirThreads * sizeof(double);
+        CUtensorMap map;
+        const bool tma = iir_tma_enabled() && make_mag_map(sc, n_items, &map);
+        LaunchScope ls(kK_nr_iir_mask, stream);
+        if (tma) k_nr_iir_mask<true><<<grid, kIirThreads, kIirStages * kIirTileBytes + 64 + ck_bytes, stream>>>(tb, cvw, cpc, item0, sc,
+                                                                                                              clean_flag, map);
+        else { std::memset(&map, 0, sizeof(map));
+               k_nr_iir_mask<false><<<grid, kIirThreads, ck_bytes, stream>>>(tb, cvw, cpc, item0, sc, clean_flag, map); }
+    }
     // output blocks of 256 samples per chunk, split evenly over CTAs of about 16 W frames
     const int max_out = std::min(cv.max_len, kNrChunk);
     const int n_blocks = (kNrPad + std::max(max_out, 1) - 1) / kNrHop - kNrPad / kNrHop + 1;

@@ -336,7 +336,7 @@ def extract_features_batch(audio, lengths=None, starts=None, sr: int = TARGET_SR
 
 
 def extract_features_host(audio: torch.Tensor, denoise: bool = True, prop_decrease: float | None = None,
-                          chunk_clips: int = 400, out_raw: torch.Tensor | None = None,
+                          chunk_clips: int | None = None, out_raw: torch.Tensor | None = None,
                           out_clean: torch.Tensor | None = None, device=None, compute_streams: int = 3):
     """End-to-end host path: equal-length clips [B, n] in (preferably pinned) HOST memory ->
     host float32 [B,149] raw (and clean).
@@ -361,6 +361,11 @@ def extract_features_host(audio: torch.Tensor, denoise: bool = True, prop_decrea
         out_clean = torch.empty((B, FEATURE_LEN), dtype=torch.float32).pin_memory()
     if B == 0:
         return (out_raw, out_clean) if denoise else out_raw
+    if chunk_clips is None:
+        # float32 samples: the copy is the bottleneck, small chunks keep the kernels close behind it; PCM-16 halves the copy
+        # and the kernels become the bottleneck, which larger launch groups serve better (measured, 10 000 3-s clips:
+        # 33.9 ms at 400 clips per chunk, 32.5 ms at 625 - 1250; tools/sweep_e2e_pcm.py)
+        chunk_clips = max(1, (800 * 48000) // max(n, 1)) if pcm_in else max(1, (400 * 48000) // max(n, 1))
     chunk = max(1, min(int(chunk_clips), B))
     head = [max(1, chunk // 4), max(1, chunk // 2)] if B >= 3 * chunk else []      # short first copies: kernels start early
     sizes, left = list(head), B - sum(head)
@@ -445,7 +450,7 @@ class PackedClips:
 
 
 def extract_features_host_packed(packed: PackedClips, denoise: bool = True, prop_decrease: float | None = None,
-                                 chunk_samples: int = 400 * 48000, out_raw: torch.Tensor | None = None,
+                                 chunk_samples: int | None = None, out_raw: torch.Tensor | None = None,
                                  out_clean: torch.Tensor | None = None, device=None, compute_streams: int = 3):
     """End-to-end host path for RAGGED clips (the real corpus: 0.45 - 10.1 s): the packed pinned buffer is pushed to the
     device back to back in chunks of about ``chunk_samples`` samples cut at clip boundaries; compute streams take the
@@ -462,6 +467,8 @@ def extract_features_host_packed(packed: PackedClips, denoise: bool = True, prop
     if B == 0:
         return (out_raw, out_clean) if denoise else out_raw
     esz = 2 if packed.pcm16 else 4
+    if chunk_samples is None:
+        chunk_samples = (800 if packed.pcm16 else 400) * 48000                   # see extract_features_host
     ends = packed.starts + ((packed.lengths.astype(np.int64) + 3) & ~3)          # padded extent of every clip in the buffer
     cuts, c0 = [], 0                                                              # (first clip, end clip, first sample, end sample)
     while c0 < B:
