@@ -31,6 +31,7 @@
 
 #include <cuda.h>                 // CUtensorMap (the encoder is fetched through cudaGetDriverEntryPoint: no libcuda link)
 
+#include "dys_async.cuh"
 #include "dys_fft.cuh"
 #include "dys_kernels.h"
 #include "dys_profile.h"
@@ -307,30 +308,6 @@ constexpr int kIirRows = 8;                          // rows per tile = rows per
 constexpr int kIirStages = DYS_IIR_STAGES;
 constexpr int kIirTileBytes = kIirRows * kIirThreads * 8;
 
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return unsigned(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, void* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-                 ::"r"(smem_u32(dst)), "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 template <bool kTma>
 __global__ void __launch_bounds__(kIirThreads)
 k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrScratch sc, int32_t* __restrict__ clean_flag,
@@ -441,7 +418,7 @@ k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
             const int row_base = li * sc.ta_max;                      // this chunk's first row in the [items x frames] matrix
             if (lane == 0) {
                 for (int s_ = 0; s_ < kIirStages; ++s_) mbar_init(&bars[s_], 1);
-                asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+                mbar_fence_init();
             }
             __syncwarp();
             if (lane == 0) {
@@ -459,7 +436,7 @@ k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
                 for (int u = 0; u < 8; ++u) a[u] = tile[(7 - u) * kIirThreads];        // a[u] = row i_ - u
                 __syncwarp();                                         // every lane holds its 8 values: the stage is free again
                 if (lane == 0 && j + kIirStages < n_batch) {
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // our reads before the engine's writes
+                    fence_proxy_async();                              // our reads before the engine's writes
                     mbar_expect_tx(&bars[st_], kIirTileBytes);
                     tma_load_2d(tiles + st_ * (kIirTileBytes / 8), &mag_map, col0, row_base + i_ - 7 - 8 * kIirStages, &bars[st_]);
                 }

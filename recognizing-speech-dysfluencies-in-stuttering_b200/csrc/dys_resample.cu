@@ -8,17 +8,19 @@
 // sample m sits at input time m * sr_in / 16000, the input is zero outside the clip, length ceil(n * 16000 / sr_in).
 //
 //   k_resample : polyphase FIR, y[m] = sum_j h[(m down) mod up][j] x[(m down) / up + j - half].
-//     A CTA stages the input span of 32 consecutive periods (one period = up' outputs = down' inputs) in shared memory;
-//     lane r of a warp owns period r, the warp owns one group of 16 consecutive phases: every input sample a lane loads
-//     (conflict-free for odd down', e.g. 441) feeds 16 FMAs, and the 16 coefficients it needs are the same for all 32
-//     lanes -- four 16-byte broadcast loads from the group's expanded table c[i][16].  5 shared-memory wavefronts per
-//     512 FMAs; accumulation in float32 in tap order.
+//     A CTA stages the input span of 64 consecutive periods (one period = up' outputs = down' inputs) in shared memory;
+//     lane r of a warp owns periods r and r + 32, the warp owns one group of 16 consecutive phases: every input sample
+//     a lane loads (conflict-free for odd down', e.g. 441) feeds 16 FMAs, and the 16 coefficients it needs are the same
+//     for all 32 lanes -- four 16-byte broadcast loads from the group's expanded table c[i][16] feed 32 FMAs per lane.
+//     6 shared-memory wavefronts per 1024 FMAs; accumulation in float32 in tap order.
 #include <algorithm>
 #include <cmath>
 #include <map>
+#include <type_traits>
 #include <mutex>
 #include <vector>
 
+#include "dys_async.cuh"
 #include "dys_error.h"
 #include "dys_kernels.h"
 #include "dys_profile.h"
@@ -29,7 +31,7 @@ namespace {
 
 constexpr double kPi = 3.14159265358979323846;
 constexpr int kGroup = 16;            // phases per warp item
-constexpr int kPeriods = 32;          // periods per CTA tile (one per lane)
+constexpr int kPeriods = 64;          // periods per CTA tile (two per lane)
 constexpr int kRsWarps = 8;
 
 double bessel_i0(double x) {
@@ -161,58 +163,102 @@ cudaError_t get_device(const RsDesign& d, RsDevice* out) {
 }
 
 struct RsParams {
-    int up2, down2, n_groups, wl, half, tile, first_off;   // first_off = -half: tile[0] is input sample period_base - half
+    int up2, down2, n_groups, wl, half, tile;
     int up, down;
 };
 
-// grid (clips, tiles of 32 periods); up to 8 warps; dynamic smem: tile floats + warps x (wl x 16) floats
+// grid (clips, tiles of 64 periods); up to 8 warps; dynamic smem: [mbarriers 128 B][input tile, kept in the input's own
+// type: 16-bit PCM tiles are half the size, which doubles the resident warps][warps x (wl x 16) coefficients].
+// Lane r of a warp owns periods r and r + 32 of the tile: 2 x 16 accumulators, so every 16-byte broadcast of
+// coefficients feeds 8 FMAs per lane and the kernel is bound by the FMA pipe, not by shared memory.
+// The tile (57 - 114 KB of contiguous input) and every group's coefficient table (18 KB) are moved by the copy engine
+// (cp.async.bulk + mbarrier): one instruction each instead of ~100 dependent load/store rounds per thread.
+template <typename TIn>
 __global__ void __launch_bounds__(kRsWarps * 32)
-k_resample(const float* __restrict__ in_f32, const int16_t* __restrict__ in_q16, const int64_t* __restrict__ in_starts,
-           const int32_t* __restrict__ in_lengths, float* __restrict__ out, const int64_t* __restrict__ out_starts,
-           const float* __restrict__ expanded, const int* __restrict__ wstart, RsParams P) {
-    extern __shared__ __align__(16) float smem[];
-    float* xt = smem;                                              // [tile]
+k_resample(const TIn* __restrict__ in, const int64_t* __restrict__ in_starts, const int32_t* __restrict__ in_lengths,
+           float* __restrict__ out, const int64_t* __restrict__ out_starts, const float* __restrict__ expanded,
+           const int* __restrict__ wstart, RsParams P) {
+    extern __shared__ __align__(128) unsigned char rs_smem[];
+    constexpr int kPer16 = 16 / int(sizeof(TIn));                   // elements per 16 bytes
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(rs_smem);        // [0] tile, [1 + warp] coefficient tables
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    float* ct = smem + ((P.tile + 3) & ~3) + warp * (P.wl * kGroup);   // this warp's expanded coefficients [wl][16]
     const int c = blockIdx.x, n_warps = blockDim.x >> 5;
     const int n_in = in_lengths[c];
     if (n_in <= 0) return;
     const long long n_out = ((long long)n_in * P.up + P.down - 1) / P.down;
     const long long per0 = (long long)blockIdx.y * kPeriods;       // first period of this tile
     if (per0 * P.up2 >= n_out) return;
-    const long long in0 = per0 * P.down2 - P.half;                 // input index of xt[0]
-    const long long src0 = in_starts[c];
-    for (int i = tid; i < P.tile; i += blockDim.x) {
-        const long long s = in0 + i;
-        float v = 0.f;
-        if (s >= 0 && s < n_in) v = in_q16 ? float(__ldg(in_q16 + src0 + s)) * (1.0f / 32768.0f) : __ldg(in_f32 + src0 + s);
-        xt[i] = v;
-    }
-    __syncthreads();
-    float* dst = out + out_starts[c];
-    for (int g = warp; g < P.n_groups; g += n_warps) {
-        const float4* src = reinterpret_cast<const float4*>(expanded + size_t(g) * P.wl * kGroup);
-        float4* c4 = reinterpret_cast<float4*>(ct);
-        __syncwarp();
-        for (int i = lane; i < P.wl * (kGroup / 4); i += 32) c4[i] = __ldg(src + i);
-        __syncwarp();
-        const float* xr = xt + lane * P.down2 + (__ldg(wstart + g) + P.half);     // window of period `lane` for this group
-        float acc[kGroup];
-#pragma unroll
-        for (int k = 0; k < kGroup; ++k) acc[k] = 0.f;
-#pragma unroll 2
-        for (int i = 0; i < P.wl; ++i) {
-            const float xv = xr[i];
-            const float4 a = c4[4 * i], b = c4[4 * i + 1], cc = c4[4 * i + 2], d = c4[4 * i + 3];
-            acc[0] = fmaf(a.x, xv, acc[0]); acc[1] = fmaf(a.y, xv, acc[1]); acc[2] = fmaf(a.z, xv, acc[2]); acc[3] = fmaf(a.w, xv, acc[3]);
-            acc[4] = fmaf(b.x, xv, acc[4]); acc[5] = fmaf(b.y, xv, acc[5]); acc[6] = fmaf(b.z, xv, acc[6]); acc[7] = fmaf(b.w, xv, acc[7]);
-            acc[8] = fmaf(cc.x, xv, acc[8]); acc[9] = fmaf(cc.y, xv, acc[9]); acc[10] = fmaf(cc.z, xv, acc[10]); acc[11] = fmaf(cc.w, xv, acc[11]);
-            acc[12] = fmaf(d.x, xv, acc[12]); acc[13] = fmaf(d.y, xv, acc[13]); acc[14] = fmaf(d.z, xv, acc[14]); acc[15] = fmaf(d.w, xv, acc[15]);
+    const long long in0 = per0 * P.down2 - P.half;                 // input index of the tile's first element
+    const TIn* src = in + in_starts[c];
+    // the tile sits in shared memory with the same 16-byte phase as its source, so that whole 16-byte units can be bulk-copied
+    const int lead = int((reinterpret_cast<uintptr_t>(src + in0) & 15u) / sizeof(TIn));
+    TIn* xt = reinterpret_cast<TIn*>(rs_smem + 128) + lead;          // xt[i] = input sample in0 + i
+    float* ct = reinterpret_cast<float*>(rs_smem + 128 + ((size_t(P.tile + kPer16) * sizeof(TIn) + 15) & ~size_t(15))) +
+                warp * (P.wl * kGroup);
+    const long long lo = max(in0, 0LL), hi = min(in0 + P.tile, (long long)n_in);       // valid input range of the tile
+    // 16-byte aligned interior [alo, ahi) of [lo, hi) goes through the copy engine, the rest (zero padding, ragged ends) by hand
+    long long alo = lo + ((kPer16 - int((reinterpret_cast<uintptr_t>(src + lo) & 15u) / sizeof(TIn))) % kPer16);
+    long long ahi = hi - int((reinterpret_cast<uintptr_t>(src + hi) & 15u) / sizeof(TIn));
+    if (ahi <= alo) { alo = hi; ahi = hi; }
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        for (int w = 0; w < n_warps; ++w) mbar_init(&bars[1 + w], 1);
+        mbar_fence_init();
+        if (ahi > alo) {
+            // the engine takes at most 2^20 - 16 bytes per copy: tiles are far below that
+            mbar_expect_tx(&bars[0], unsigned((ahi - alo) * sizeof(TIn)));
+            bulk_copy_g2s(xt + (alo - in0), src + alo, unsigned((ahi - alo) * sizeof(TIn)), &bars[0]);
         }
-        const long long m0 = (per0 + lane) * P.up2 + (long long)g * kGroup;
+    }
+    for (long long s_ = in0 + tid; s_ < in0 + P.tile; s_ += blockDim.x) {
+        if (s_ >= alo && s_ < ahi) { s_ += ((ahi - s_ - 1) / blockDim.x) * blockDim.x; continue; }   // skip the engine's part
+        xt[s_ - in0] = (s_ >= lo && s_ < hi) ? __ldg(src + s_) : TIn(0);
+    }
+    __syncthreads();                                                 // barriers initialised, hand-written part in place
+    if (ahi > alo) mbar_wait(&bars[0], 0);
+    constexpr float kScale = std::is_same<TIn, int16_t>::value ? (1.0f / 32768.0f) : 1.0f;   // PCM-16: value = q / 32768 (exact)
+    float* dst = out + out_starts[c];
+    unsigned phase = 0;
+    for (int g = warp; g < P.n_groups; g += n_warps, phase ^= 1u) {
+        float4* c4 = reinterpret_cast<float4*>(ct);
+        __syncwarp();                                                // every lane is done with the previous table
+        if (lane == 0) {
+            fence_proxy_async();
+            mbar_expect_tx(&bars[1 + warp], unsigned(P.wl * kGroup * 4));
+            bulk_copy_g2s(ct, expanded + size_t(g) * P.wl * kGroup, unsigned(P.wl * kGroup * 4), &bars[1 + warp]);
+        }
+        const TIn* xa = xt + lane * P.down2 + (__ldg(wstart + g) + P.half);     // window of period `lane` for this group
+        const TIn* xb = xa + 32 * P.down2;                                      // ... and of period lane + 32
+        float acc[2][kGroup];
 #pragma unroll
-        for (int k = 0; k < kGroup; ++k)
-            if (m0 + k < n_out) dst[m0 + k] = acc[k];
+        for (int k = 0; k < kGroup; ++k) { acc[0][k] = 0.f; acc[1][k] = 0.f; }
+        mbar_wait(&bars[1 + warp], phase);
+        // software pipeline: the loads of tap i + 1 are issued before the 32 FMAs of tap i
+        float4 q0 = c4[0], q1 = c4[1], q2 = c4[2], q3 = c4[3];
+        TIn ra = xa[0], rb = xb[0];
+        for (int i = 0; i < P.wl; ++i) {
+            const int nx = min(i + 1, P.wl - 1);
+            const float4 n0 = c4[4 * nx], n1 = c4[4 * nx + 1], n2 = c4[4 * nx + 2], n3 = c4[4 * nx + 3];
+            const TIn na = xa[nx], nb = xb[nx];
+            const float va = float(ra) * kScale, vb = float(rb) * kScale;
+            const float w[kGroup] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+#pragma unroll
+            for (int k = 0; k < kGroup; ++k) { acc[0][k] = fmaf(w[k], va, acc[0][k]); acc[1][k] = fmaf(w[k], vb, acc[1][k]); }
+            q0 = n0; q1 = n1; q2 = n2; q3 = n3; ra = na; rb = nb;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const long long m0 = (per0 + lane + 32 * h) * P.up2 + (long long)g * kGroup;
+            if (m0 + kGroup <= n_out && ((reinterpret_cast<uintptr_t>(dst + m0) & 15u) == 0)) {
+#pragma unroll
+                for (int k = 0; k < kGroup; k += 4)
+                    *reinterpret_cast<float4*>(dst + m0 + k) = make_float4(acc[h][k], acc[h][k + 1], acc[h][k + 2], acc[h][k + 3]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < kGroup; ++k)
+                    if (m0 + k < n_out) dst[m0 + k] = acc[h][k];
+            }
+        }
     }
 }
 
@@ -240,21 +286,25 @@ cudaError_t launch_resample(const float* in_f32, const int16_t* in_q16, int sr_i
     if (cudaError_t e = get_device(*d, &dv)) return e;
     RsParams P;
     P.up2 = d->up2; P.down2 = d->down2; P.n_groups = d->n_groups; P.wl = d->wl; P.half = d->half; P.tile = d->tile;
-    P.first_off = -d->half; P.up = d->up; P.down = d->down;
-    const size_t tile_b = size_t((d->tile + 3) & ~3) * 4, table_b = size_t(d->wl) * kGroup * 4;
+    P.up = d->up; P.down = d->down;
+    const size_t esz = in_q16 ? 2 : 4;
+    const size_t tile_b = 128 + ((size_t(d->tile) * esz + 16 + 15) & ~size_t(15)), table_b = size_t(d->wl) * kGroup * 4;
     if (tile_b + table_b > 227 * 1024) return cudaErrorInvalidValue;
     const int n_warps = int(std::max<size_t>(1, std::min<size_t>(std::min(kRsWarps, d->n_groups), (227 * 1024 - tile_b) / table_b)));
     const size_t smem = tile_b + size_t(n_warps) * table_b;
     static std::mutex attr_mu;
     {
         std::lock_guard<std::mutex> lock(attr_mu);
-        if (cudaError_t e = cudaFuncSetAttribute(k_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) return e;
+        if (cudaError_t e = in_q16 ? cudaFuncSetAttribute(k_resample<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))
+                                   : cudaFuncSetAttribute(k_resample<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem))) return e;
     }
     const long long max_out = ((long long)max_in_len * d->up + d->down - 1) / d->down;
     const int tiles = int((max_out + (long long)kPeriods * d->up2 - 1) / ((long long)kPeriods * d->up2));
     LaunchScope ls(kK_resample, stream);
-    k_resample<<<dim3(n_clips, tiles), n_warps * 32, smem, stream>>>(in_f32, in_q16, in_starts, in_lengths, out, out_starts,
-                                                                       dv.expanded, dv.wstart, P);
+    if (in_q16) k_resample<int16_t><<<dim3(n_clips, tiles), n_warps * 32, smem, stream>>>(in_q16, in_starts, in_lengths, out, out_starts,
+                                                                                           dv.expanded, dv.wstart, P);
+    else k_resample<float><<<dim3(n_clips, tiles), n_warps * 32, smem, stream>>>(in_f32, in_starts, in_lengths, out, out_starts,
+                                                                                  dv.expanded, dv.wstart, P);
     return cudaGetLastError();
 }
 

@@ -8,6 +8,10 @@ tracing.  CPU tensors are rejected -- there is no CPU implementation.
     raw, status              = torch.ops.dysb200.features_raw(audio, starts, lengths, max_len)
     raw, clean, status       = torch.ops.dysb200.features_raw_clean(audio, starts, lengths, max_len, prop_decrease)
     qc                       = torch.ops.dysb200.qc_metrics(audio, starts, lengths, max_len)
+    audio16k                 = torch.ops.dysb200.resample_to_16k(audio, starts, lengths, max_len, sr_in, out_starts, total_out)
+
+``audio`` may be float32 or int16 (PCM-16, value = q / 32768: the library's *_pcm16 entry points) for the feature
+operators and the rate converter.
 
 Row i of ``raw`` is the reference's ``extract_features(clip_i, 16000)`` (pipeline1.py:257-265); ``clean`` is the same
 function applied to the clip after ``clean_audio_and_cache`` (pipeline1.py:126-146).
@@ -37,7 +41,7 @@ def features_raw(audio: torch.Tensor, starts: torch.Tensor, lengths: torch.Tenso
 @features_raw.register_fake
 def _(audio, starts, lengths, max_len):
     n = starts.shape[0]
-    return audio.new_empty((n, FEATURE_LEN)), lengths.new_empty((n,), dtype=torch.int32)
+    return audio.new_empty((n, FEATURE_LEN), dtype=torch.float32), lengths.new_empty((n,), dtype=torch.int32)
 
 
 @torch.library.custom_op("dysb200::features_raw_clean", mutates_args=(), device_types="cuda")
@@ -52,7 +56,7 @@ def features_raw_clean(audio: torch.Tensor, starts: torch.Tensor, lengths: torch
 @features_raw_clean.register_fake
 def _(audio, starts, lengths, max_len, prop_decrease):
     n = starts.shape[0]
-    return (audio.new_empty((n, FEATURE_LEN)), audio.new_empty((n, FEATURE_LEN)),
+    return (audio.new_empty((n, FEATURE_LEN), dtype=torch.float32), audio.new_empty((n, FEATURE_LEN), dtype=torch.float32),
             lengths.new_empty((2 * n,), dtype=torch.int32))
 
 
@@ -78,3 +82,31 @@ def qc_metrics(audio: torch.Tensor, starts: torch.Tensor, lengths: torch.Tensor,
 @qc_metrics.register_fake
 def _(audio, starts, lengths, max_len):
     return audio.new_empty((starts.shape[0], 3))
+
+
+@torch.library.custom_op("dysb200::resample_to_16k", mutates_args=(), device_types="cuda")
+def resample_to_16k(audio: torch.Tensor, starts: torch.Tensor, lengths: torch.Tensor, max_len: int, sr_in: int,
+                    out_starts: torch.Tensor, total_out: int) -> torch.Tensor:
+    """The rate-conversion half of librosa.load(path, sr=16000) (pipeline1.py:102): clip i (``lengths[i]`` samples at
+    ``starts[i]``, ``sr_in`` Hz) -> ceil(lengths[i] * 16000 / sr_in) float32 samples at ``out_starts[i]`` of the result."""
+    _need_cuda(audio, starts, lengths, out_starts)
+    lib = _lib.load()
+    dev = audio.device
+    out = torch.zeros((int(total_out),), dtype=torch.float32, device=dev)
+    n = int(starts.shape[0])
+    if n == 0:
+        return out
+    if audio.dtype not in (torch.float32, torch.int16):
+        raise DysError("audio must be float32 or int16")
+    with torch.cuda.device(dev):
+        _lib.check(lib.dys_init(), "dys_init")
+        a, s, ln, os_ = audio.contiguous(), starts.contiguous(), lengths.contiguous(), out_starts.contiguous()
+        _lib.check(lib.dys_resample_to_16k(a.data_ptr(), 1 if a.dtype == torch.int16 else 0, int(sr_in), s.data_ptr(), ln.data_ptr(),
+                                           n, int(max_len), out.data_ptr(), os_.data_ptr(),
+                                           torch.cuda.current_stream(dev).cuda_stream), "dys_resample_to_16k")
+    return out
+
+
+@resample_to_16k.register_fake
+def _(audio, starts, lengths, max_len, sr_in, out_starts, total_out):
+    return audio.new_empty((total_out,), dtype=torch.float32)

@@ -147,7 +147,7 @@ def test_torch_operators_are_registered_and_have_no_cpu_kernel(pkg):
     import torch
     from torch._subclasses.fake_tensor import FakeTensorMode
     pkg.torch_ops                                                   # registers the operators
-    for name in ("features_raw", "features_raw_clean", "qc_metrics"):
+    for name in ("features_raw", "features_raw_clean", "qc_metrics", "resample_to_16k"):
         assert hasattr(torch.ops.dysb200, name)
     with FakeTensorMode():
         a = torch.empty(1000, device="cuda")

@@ -291,3 +291,43 @@ def test_ragged_host_streaming_equals_device_path(fe, synth, torch_cuda):
         h_raw, h_clean = fe.extract_features_host_packed(packed, denoise=True, chunk_samples=600000)
         assert torch.equal(h_raw, ref_raw.cpu()) and torch.equal(h_clean, ref_clean.cpu())
         assert torch.equal(fe.extract_features_host_packed(packed, denoise=False, chunk_samples=10 ** 9), ref_raw.cpu())
+
+
+def test_torch_ops_take_pcm16_and_resample(fe, pkg, synth, torch_cuda):
+    torch = torch_cuda
+    pkg.torch_ops
+    q = torch.from_numpy(np.stack([owav.quantize_pcm16(synth.synth_clip(900 + i, 22050)) for i in range(3)])).cuda()
+    n, L = q.shape
+    starts = torch.arange(n, dtype=torch.int64, device="cuda") * L
+    lens = torch.full((n,), L, dtype=torch.int32, device="cuda")
+    raw, clean, st = torch.ops.dysb200.features_raw_clean(q.reshape(-1), starts, lens, L, 1.0)
+    ref_raw, ref_clean = fe.extract_features_batch(q, denoise=True)
+    assert torch.equal(raw, ref_raw) and torch.equal(clean, ref_clean)
+    out_len = 16000
+    out_starts = torch.arange(n, dtype=torch.int64, device="cuda") * out_len
+    y = torch.ops.dysb200.resample_to_16k(q.reshape(-1), starts, lens, L, 22050, out_starts, n * out_len)
+    ref = fe.resample_to_16k([q[i].cpu().numpy() for i in range(n)], 22050)
+    for i in range(n):
+        np.testing.assert_array_equal(y[i * out_len:(i + 1) * out_len].cpu().numpy(), ref[i])
+
+
+def test_bulk_tensor_variant_of_the_gate_sweep_gives_the_same_pcm(fe, synth, tmp_path, torch_cuda):
+    """DYS_IIR_TMA=1 routes k_nr_iir_mask's backward sweep through cp.async.bulk.tensor + mbarrier (opt-in, measured slower):
+    same PCM, same vectors.  The switch is read once per process, hence the child process."""
+    import subprocess
+    clips = [synth.synth_clip(40 + i, n) for i, n in enumerate((48000, 30011, 70000, 9000))]
+    raw, clean, st, pcm = fe.extract_features_batch(clips, denoise=True, return_status=True, return_pcm=True)
+    np.savez(tmp_path / "ref.npz", clean=clean.cpu().numpy(), pcm=np.concatenate([p.cpu().numpy() for p in pcm]))
+    code = f"""
+import sys, numpy as np
+sys.path.insert(0, {ROOT!r})
+import dysb200 as pkg
+clips = [pkg.synth.synth_clip(40 + i, n) for i, n in enumerate((48000, 30011, 70000, 9000))]
+raw, clean, st, pcm = pkg.frontend.extract_features_batch(clips, denoise=True, return_status=True, return_pcm=True)
+ref = np.load({str(tmp_path / 'ref.npz')!r})
+assert np.array_equal(clean.cpu().numpy(), ref['clean']) and np.array_equal(np.concatenate([p.cpu().numpy() for p in pcm]), ref['pcm'])
+print('tma ok')
+"""
+    env = dict(os.environ, DYS_IIR_TMA="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "tma ok" in out.stdout, out.stderr[-2000:]
