@@ -48,14 +48,14 @@ namespace {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 // Launch groups with at least this many chunks fill the machine twice over with ONE CTA per chunk: k_nr_stft_mag then
-// gives a CTA 192 frames instead of 64 (its 24 KB of tables are loaded once per CTA: -2 %) and k_nr_apply_ola 24 rounds
+// gives a CTA 256 frames instead of 64 (its 24 KB of tables are loaded once per CTA: -2 %) and k_nr_apply_ola 24 rounds
 // instead of 8 (no frames transformed twice at CTA seams: -1.6 %).  Smaller groups keep the short CTAs: a single clip's
 // latency is set by how many SMs its frames spread over.
 constexpr int kBigGroup = 592;
-constexpr int kFramesPerCtaSmall = 64, kFramesPerCtaBig = 192;
+constexpr int kFramesPerCtaSmall = 64, kFramesPerCtaBig = 256;   // powers of two: the check-point tests of the sweep are masks
 constexpr int kIirSegShift = 6;
 constexpr int kIirSeg = 1 << kIirSegShift;           // frames per forward-IIR interval = check-point spacing of the backward sweep
-static_assert(kFramesPerCtaSmall % kIirSeg == 0 && kFramesPerCtaBig % kIirSeg == 0, "CTAs must own whole intervals");
+static_assert(kFramesPerCtaSmall == 1 << 6 && kFramesPerCtaBig == 1 << 8, "launch_denoise passes the shifts 6 / 8 to k_nr_iir_mask");
 
 struct NrGeom {
     int clip, n, c0, out_len, L, Tn, t_first, t_last;
@@ -229,16 +229,17 @@ k_nr_stft_mag(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
     double* mag = sc.mag + size_t(li) * sc.ta_max * kNrBinsPad;
     double2* spec = sc.spec + size_t(li) * sc.ta_max * kNrBinsPad;
     // Forward half of filtfilt([b], [1, b - 1]) -- f[t] = b A[t] + r f[t-1], r = 1 - b -- without a sweep of its own: the
-    // recursion is linear, so over an interval of kIirSeg frames  f[end] = r^len f[start - 1] + sum_u b A[u] r^(len-1-u).
-    // Each warp keeps the Horner sum over ITS frames of the interval (every 8th: acc <- r^8 acc + b |D|) while the
-    // magnitudes are still in registers; at the interval's end the 8 sums are weighted (r^0..r^7), added in warp order
-    // through the FFT tiles and stored: 4 KB per 64 frames instead of re-reading the 0.27 MB of |D| they cover.
-    // k_nr_iir_mask chains the intervals (check-points of its backward sweep).
+    // recursion is linear, so over the CTA's interval of frames  f[end] = r^len f[start - 1] + sum_u b A[u] r^(len-1-u).
+    // Each warp keeps the Horner sum over ITS frames (every 8th: acc <- r^8 acc + b |D|) while the magnitudes are still
+    // in registers; when the CTA is through, the 8 sums are weighted (r^0..r^7), added in warp order through the FFT
+    // tiles and stored: 4 KB per CTA instead of re-reading the |D| rows it wrote (0.27 - 0.8 MB).  One interval per
+    // CTA: the only block-wide barrier sits where the warps finish anyway (a barrier every 64 frames cost 0.2 ms).
+    // k_nr_iir_mask chains the intervals (they are the check-points of its backward sweep).
     const double iir_b = tb.iir_b, iir_r = 1.0 - iir_b;
     double r8 = iir_r * iir_r; r8 *= r8; r8 *= r8;
     double* part = sc.part + size_t(li) * sc.n_seg_max * kNrBinsPad;
-    for (int t0 = t_begin; t0 < t_end; t0 += kIirSeg) {
-        const int seg_len = min(kIirSeg, t_end - t0);
+    {
+        const int t0 = t_begin, seg_len = t_end - t_begin;
         double acc[16], acc_nyq = 0.0;
 #pragma unroll
         for (int q = 0; q < 16; ++q) acc[q] = 0.0;
@@ -278,21 +279,19 @@ k_nr_stft_mag(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
         });
         if (lane == 0) pub[512] = acc_nyq * w;
         __syncthreads();
-        double* prow = part + size_t((t0 - g.t_first) / kIirSeg) * kNrBinsPad;
+        double* prow = part + size_t(blockIdx.y) * kNrBinsPad;
         for (int k = tid; k < kNrBins; k += kThreads) {
             double sum = 0.0;
 #pragma unroll
             for (int w2 = 0; w2 < kWarps; ++w2) sum += reinterpret_cast<const double*>(sm.xbuf[w2])[k];
             prow[k] = sum;
         }
-        __syncthreads();
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // filtfilt([b], [1, b - 1]) over time + sigmoid + 7-tap time smoothing, one thread per bin.
 constexpr int kIirThreads = 32;
-constexpr int kIirCkShift = kIirSegShift;            // forward state known at the end of every interval of k_nr_stft_mag
 constexpr int kIirMaxSeg = 48;                       // covers ta_max <= 3072 (a full 660 000-sample chunk has 2579)
 
 // ---- bulk-tensor (TMA) ring for the backward sweep ------------------------------------------------------------------
@@ -311,7 +310,7 @@ constexpr int kIirTileBytes = kIirRows * kIirThreads * 8;
 template <bool kTma>
 __global__ void __launch_bounds__(kIirThreads)
 k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrScratch sc, int32_t* __restrict__ clean_flag,
-              const __grid_constant__ CUtensorMap mag_map) {
+              int seg_shift, const __grid_constant__ CUtensorMap mag_map) {
     extern __shared__ __align__(128) unsigned char iir_smem[];
     // kTma: [kIirStages tiles of 8 x 32 doubles][kIirStages mbarriers], then in both cases
     // ck[n_seg_max][kIirThreads]: f at the last frame of every interval
@@ -330,18 +329,22 @@ k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
     // k_nr_stft_mag left  sum_u b A[u] r^(len-1-u)  per interval: chain them,  f[end] = r^len f[start-1] + sum.
     double prev = (g.t_first == 0) ? col[0] : 0.0;
     {
-        double rseg = r;                              // r^kIirSeg by squaring
-#pragma unroll
-        for (int e = 0; e < kIirSegShift; ++e) rseg *= rseg;
+        const int seg = 1 << seg_shift;               // frames per CTA of k_nr_stft_mag: 64 or 256
+        double rseg = r;                              // r^seg by squaring
+        for (int e = 0; e < seg_shift; ++e) rseg *= rseg;
         const double* part = sc.part + size_t(li) * sc.n_seg_max * P + k;
-        const int n_seg = (Ta + kIirSeg - 1) >> kIirSegShift;
+        const int n_seg = (Ta + seg - 1) >> seg_shift;
         double pnext = part[0];
         for (int j = 0; j < n_seg; ++j) {
             const double pj = pnext;
             if (j + 1 < n_seg) pnext = part[size_t(j + 1) * P];
-            const int len = min(kIirSeg, Ta - (j << kIirSegShift));
+            const int len = min(seg, Ta - (j << seg_shift));
             double rl = rseg;
-            if (len < kIirSeg) { rl = 1.0; for (int e = 0; e < len; ++e) rl *= r; }
+            if (len < seg) {                          // the last, partial interval: r^len by squaring
+                rl = 1.0;
+                double sq = r;
+                for (int e = len; e > 0; e >>= 1, sq *= sq) if (e & 1) rl *= sq;
+            }
             prev = fma(rl, prev, pj);
             ck[j][threadIdx.x] = prev;
         }
@@ -369,7 +372,7 @@ k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
     double fcur = prev;                               // f[Ta-1]
     bool bad = false;
     // backward: S[t] = b f[t] + (1 - b) S[t+1]; the forward state is re-derived as f[t-1] = (f[t] - b A[t]) / (1 - b)
-    // (error growth (1/r)^128 = 2.8 between check-points); row i+3 of the time-smoothed mask is complete once
+    // (error growth (1/r)^256 = 7.7 between check-points); row i+3 of the time-smoothed mask is complete once
     // the raw mask of row i is known, and overwrites |D| in place (row i+3 was consumed three steps earlier).
     auto emit = [&](int row, double m0) {                // push the raw mask of row - 3, write the smoothed row
 #pragma unroll
@@ -388,9 +391,10 @@ k_nr_iir_mask(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
         bad |= isnan(m0);
         return m0;
     };
+    const int seg_mask = (1 << seg_shift) - 1;
     auto rewind = [&](int i_, double A) {                 // f[i_ - 1] from f[i_]
         if (i_ > 0) {
-            if ((i_ & ((1 << kIirCkShift) - 1)) == 0) fcur = ck[(i_ >> kIirCkShift) - 1][threadIdx.x];
+            if ((i_ & seg_mask) == 0) fcur = ck[(i_ >> seg_shift) - 1][threadIdx.x];
             else fcur = (fcur - b * A) * rinv;
         }
     };
@@ -877,9 +881,9 @@ cudaError_t launch_denoise(const DeviceTables& tb, const ClipView& cv, float* cl
         const bool tma = iir_tma_enabled() && make_mag_map(sc, n_items, &map);
         LaunchScope ls(kK_nr_iir_mask, stream);
         if (tma) k_nr_iir_mask<true><<<grid, kIirThreads, kIirStages * kIirTileBytes + 64 + ck_bytes, stream>>>(tb, cvw, cpc, item0, sc,
-                                                                                                              clean_flag, map);
+                                                                                                              clean_flag, big ? 8 : 6, map);
         else { std::memset(&map, 0, sizeof(map));
-               k_nr_iir_mask<false><<<grid, kIirThreads, ck_bytes, stream>>>(tb, cvw, cpc, item0, sc, clean_flag, map); }
+               k_nr_iir_mask<false><<<grid, kIirThreads, ck_bytes, stream>>>(tb, cvw, cpc, item0, sc, clean_flag, big ? 8 : 6, map); }
     }
     // output blocks of 256 samples per chunk, split evenly over CTAs of about 16 W frames
     const int max_out = std::min(cv.max_len, kNrChunk);
