@@ -62,6 +62,10 @@ template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
 // Shared-memory loads the compiler may neither duplicate nor re-issue: under register pressure ptxas
 // re-materialises plain LDS (two copies of every partner / table load in the real-FFT split), which
 // costs wavefronts on the unit these kernels are bound by.
+// Ordering: the asm is volatile but carries no "memory" clobber on purpose (a clobber would also pin every
+// independent load and store around it).  Every use reads data that other lanes stored BEFORE a __syncwarp() and
+// is followed by a __syncwarp() before the location is overwritten; __syncwarp() is the compiler-level and
+// hardware-level fence that orders the plain stores against these loads.
 __device__ __forceinline__ double2 lds_once(const double2* p) {
     double2 r;
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(unsigned(__cvta_generic_to_shared(p))));

@@ -1,6 +1,7 @@
 #include "dys_profile.h"
 
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <vector>
 
@@ -15,7 +16,7 @@ const char* const kNames[kKernelCount] = {
     "k_qc_snr", "k_qc_hf_bins", "k_qc_finish", "k_qc_flatness", "k_qc_flat_reduce", "k_resample"};
 
 struct Record {
-    int id;
+    int id, dev;
     cudaEvent_t start, stop;
 };
 
@@ -23,13 +24,14 @@ std::atomic<long long> g_launches[kKernelCount];
 std::atomic<bool> g_enabled{false};
 std::mutex g_mu;
 std::vector<Record> g_records;          // events in flight (not yet read)
-std::vector<cudaEvent_t> g_free;        // recycled events
+std::map<int, std::vector<cudaEvent_t>> g_free;   // recycled events, per device (an event belongs to the device it was created on)
 double g_ms[kKernelCount] = {};
 
-cudaEvent_t take_event() {
-    if (!g_free.empty()) {
-        cudaEvent_t e = g_free.back();
-        g_free.pop_back();
+cudaEvent_t take_event(int dev) {
+    std::vector<cudaEvent_t>& pool = g_free[dev];
+    if (!pool.empty()) {
+        cudaEvent_t e = pool.back();
+        pool.pop_back();
         return e;
     }
     cudaEvent_t e = nullptr;
@@ -41,21 +43,21 @@ cudaEvent_t take_event() {
 
 const char* kernel_name(int id) { return (id >= 0 && id < kKernelCount) ? kNames[id] : ""; }
 
-LaunchScope::LaunchScope(int id, cudaStream_t stream) : slot_(-1), stream_(stream) {
+LaunchScope::LaunchScope(int id, cudaStream_t stream) : stop_(nullptr), stream_(stream) {
     g_launches[id].fetch_add(1, std::memory_order_relaxed);
     if (!g_enabled.load(std::memory_order_relaxed)) return;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
     std::lock_guard<std::mutex> lock(g_mu);
-    Record r{id, take_event(), take_event()};
+    Record r{id, dev, take_event(dev), take_event(dev)};
     if (!r.start || !r.stop) return;
     cudaEventRecord(r.start, stream);
-    slot_ = int(g_records.size());
+    stop_ = r.stop;                      // the handle, not an index: profile_read may clear g_records from another thread
     g_records.push_back(r);
 }
 
 LaunchScope::~LaunchScope() {
-    if (slot_ < 0) return;
-    std::lock_guard<std::mutex> lock(g_mu);
-    cudaEventRecord(g_records[slot_].stop, stream_);
+    if (stop_) cudaEventRecord(stop_, stream_);
 }
 
 void profile_enable(bool on) { g_enabled.store(on); }
@@ -69,8 +71,8 @@ cudaError_t profile_read(double* ms, long long* launches, int reset) {
         if (e == cudaSuccess) e = cudaEventElapsedTime(&t, r.start, r.stop);
         if (e == cudaSuccess) g_ms[r.id] += double(t);
         else err = e;
-        g_free.push_back(r.start);
-        g_free.push_back(r.stop);
+        g_free[r.dev].push_back(r.start);
+        g_free[r.dev].push_back(r.stop);
     }
     g_records.clear();
     for (int i = 0; i < kKernelCount; ++i) {

@@ -42,7 +42,7 @@ public:
     LaunchScope(const LaunchScope&) = delete;
     LaunchScope& operator=(const LaunchScope&) = delete;
 private:
-    int slot_;
+    cudaEvent_t stop_;
     cudaStream_t stream_;
 };
 
