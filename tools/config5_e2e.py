@@ -99,8 +99,15 @@ def main():
     torch.cuda.synchronize()
     t_cmvn = time.perf_counter() - w0
     w0 = time.perf_counter()
-    pred = rf.predict(train_sc.to_sklearn().transform(clean.cpu().numpy()))     # main1.py:987-989: the training scaler
+    Zc = train_sc.to_sklearn().transform(clean.cpu().numpy())                   # main1.py:987-989: the training scaler
+    pred_par = rf.predict(Zc)                                                   # n_jobs=-1 like the reference (main1.py:862)
     t_rf = time.perf_counter() - w0
+    # scikit-learn adds the trees' probabilities in thread-completion order: with n_jobs=-1 near-ties between two classes flip
+    # from run to run ON THE SAME MATRIX (that, not the features, is why round 1's 1-GPU and 8-GPU class counts differed by
+    # ~60 in 1e6).  The counts reported for the 1-GPU / 8-GPU comparison use the single-thread, fixed-order sum.
+    par_counts = [np.bincount(pred_par, minlength=3).tolist(), np.bincount(rf.predict(Zc), minlength=3).tolist()]
+    rf.set_params(n_jobs=1)
+    pred = rf.predict(Zc)
     counts = np.bincount(pred, minlength=3).astype(np.float64)
     stats = torch.tensor([t_feat, t_gen, t_cmvn, t_rf, float(hi - lo)], dtype=torch.float64, device=dev)
     cls = torch.from_numpy(counts).to(dev)
@@ -124,6 +131,7 @@ def main():
                 "feature_extraction_s": t_feat, "audio_sec_per_sec_features": total * 3.0 / t_feat,
                 "on_device_generation_s": t_gen, "global_cmvn_fit_and_apply_s": t_cmvn,
                 "classifier_predict_s_cpu": t_rf, "predicted_class_counts": cls.tolist(),
+                "rank0_counts_of_two_parallel_predicts_of_the_same_rows": par_counts,
                 "scaler_mean_first3": scaler.mean_[:3].tolist(),
                 "feature_bits_fingerprint": {"raw_sum": int(sums[0]), "clean_sum": int(sums[1]), "raw_hash": int(sums[2]),
                                              "clean_hash": int(sums[3])},
