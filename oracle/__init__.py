@@ -21,9 +21,13 @@ Parity status
   reference within atol 1e-3 / rtol 1e-4 (tests/test_oracle_golden.py).
 * CMVN (StandardScaler)      : PINNED  -- reproduces output_results/scaler_after.pkl.
 * normalise + PCM-16 quantise: pinned by property (every committed WAV peaks at full scale).
-* denoise (noisereduce)      : PARITY UNPINNED -- noisereduce is not installable in
-  the build container and the reference's golden inputs for it are MP3 (no decoder
-  here).  oracle/denoise.py restates noisereduce 3.x's non-stationary spectral gate
-  from its published algorithm, calling the very same scipy routines it calls
-  (scipy.signal.filtfilt, scipy.signal.fftconvolve).
+* denoise (noisereduce)      : PINNED STATISTICALLY -- noisereduce is not installable in
+  the build container; oracle/denoise.py restates its non-stationary spectral gate from
+  the published algorithm (same scipy routines: filtfilt, fftconvolve) and reproduces the
+  reference's 888 mp3 -> clear_audio/*.wav pairs to a median 70.9 dB, with every perturbed
+  default 25 - 50 dB worse on every clip (tests/test_denoise_pin.py).
+* load (librosa.load)        : lengths PINNED exactly (888/888, libmpg123's gapless trimming +
+  ceil), samples statistically: oracle/resample.py restates soxr's published HQ recipe
+  (soxr itself stays unpinned); MP3 frames are decoded by the FFmpeg libavcodec that
+  ships in the image (recognizing-speech-dysfluencies-in-stuttering_b200/mp3io.py).
 """

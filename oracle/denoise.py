@@ -1,4 +1,4 @@
-"""Oracle: the reference's cleaning step.  TEST INFRASTRUCTURE ONLY.  PARITY UNPINNED.
+"""Oracle: the reference's cleaning step.  TEST INFRASTRUCTURE ONLY.  PARITY: PINNED STATISTICALLY (see below).
 
 Follows /root/reference/pipeline1.py:126-146 (``clean_audio_and_cache``):
 
@@ -8,15 +8,21 @@ Follows /root/reference/pipeline1.py:126-146 (``clean_audio_and_cache``):
     ... later  librosa.load(cleaned)               # :389 / :437  int16/32768
 
 ``noisereduce`` (requirements.txt:6, unpinned; 3.x API) is NOT vendored in the
-reference and NOT installable here, and the reference's golden inputs for this step
-are MP3 (no decoder in this image).  This file therefore restates the published
+reference and NOT installable here.  This file therefore restates the published
 algorithm of noisereduce 3.0.x ``SpectralGateNonStationary`` with the defaults that
 ``reduce_noise(y, sr)`` selects (stationary=False, prop_decrease=1.0, n_fft=1024,
 hop=256, time_constant_s=2.0, freq_mask_smooth_hz=500, time_mask_smooth_ms=50,
 thresh_n_mult_nonstationary=2, sigmoid_slope_nonstationary=10, chunk_size=600000,
 padding=30000), calling the same scipy routines noisereduce calls
 (scipy.signal.filtfilt, scipy.signal.fftconvolve) and librosa-equivalent STFT/ISTFT.
-What IS checked against the reference's artefacts: length preservation and the
+What IS checked against the reference's artefacts (tests/test_denoise_pin.py, whole corpus in
+profiles/r02_denoise_pin_corpus.json): the reference's 888 ``segrigated_samples/**.mp3 ->
+clear_audio/*.wav`` pairs.  Decoded (FFmpeg mp3float with libmpg123's trimming) and resampled
+(oracle/resample.py), the output of this file agrees with the reference's WAV samples to a median
+70.9 dB (5th percentile 57.2 dB) -- about half an LSB rms -- and every single default moved off its
+value (n_grad_freq, n_grad_time, threshold, slope, time constant, prop_decrease) drops that by
+25 - 50 dB on every clip.  Bit-exactness is out of reach for two named reasons: another MP3 decoder
+implementation and a restated (not linked) soxr filter.  Also: length preservation and the
 full-scale peak of every committed clear_audio/*.wav (normalise + quantise).
 """
 from __future__ import annotations
