@@ -634,7 +634,10 @@ def _decode_file(path: str):
     if ext == ".mp3":
         return mp3io.read_mp3(path)
     if ext == ".wav":
-        return wavio.read_wav_pcm16(path)
+        try:
+            return wavio.read_wav_pcm16(path)           # mono PCM-16 stays 16-bit
+        except ValueError:
+            return wavio.read_wav(path)                 # other widths / float / multi-channel: float32 mono like librosa
     raise ValueError(f"unsupported audio format {ext!r} (WAV/PCM-16 and MP3 are decoded here)")
 
 

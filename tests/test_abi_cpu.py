@@ -168,3 +168,33 @@ def test_numa_binding_helper_never_raises(pkg):
     assert isinstance(r, dict) and ("skipped" in r or "node" in r)
     if "skipped" in r:
         assert os.sched_getaffinity(0) == before
+
+
+def test_wav_reader_covers_libsndfile_encodings_and_mono_mixdown(pkg, tmp_path):
+    """load_audio's WAV side (pipeline1.py:102: soundfile -> float32, librosa mono=True = mean over channels)."""
+    import struct
+    rng = np.random.default_rng(0)
+
+    def write(path, codec, bits, channels, payload, sr=16000):
+        blk = channels * bits // 8
+        hdr = b"RIFF" + struct.pack("<I", 36 + len(payload)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, codec, channels, sr, sr * blk, blk, bits)
+        open(path, "wb").write(hdr + b"data" + struct.pack("<I", len(payload)) + payload)
+
+    q = rng.integers(-32768, 32767, size=(500, 2)).astype("<i2")
+    write(tmp_path / "st16.wav", 1, 16, 2, q.tobytes())
+    y, sr = pkg.wavio.read_wav(str(tmp_path / "st16.wav"))
+    assert sr == 16000 and y.dtype == np.float32
+    np.testing.assert_array_equal(y, (q.astype(np.float32) / np.float32(32768.0)).mean(axis=1, dtype=np.float32))
+    with pytest.raises(ValueError):
+        pkg.wavio.read_wav_pcm16(str(tmp_path / "st16.wav"))
+    f = rng.standard_normal(300).astype("<f4")
+    write(tmp_path / "f32.wav", 3, 32, 1, f.tobytes(), sr=22050)
+    y, sr = pkg.wavio.read_wav(str(tmp_path / "f32.wav"))
+    assert sr == 22050 and np.array_equal(y, f)
+    q24 = rng.integers(-(1 << 23), (1 << 23) - 1, size=200)
+    payload = b"".join(int(v & 0xFFFFFF).to_bytes(3, "little") for v in q24)
+    write(tmp_path / "p24.wav", 1, 24, 1, payload)
+    np.testing.assert_array_equal(pkg.wavio.read_wav(str(tmp_path / "p24.wav"))[0], (q24 / float(1 << 23)).astype(np.float32))
+    u8 = rng.integers(0, 255, size=100).astype(np.uint8)
+    write(tmp_path / "u8.wav", 1, 8, 1, u8.tobytes())
+    np.testing.assert_array_equal(pkg.wavio.read_wav(str(tmp_path / "u8.wav"))[0], (u8.astype(np.float32) - 128) / 128)
