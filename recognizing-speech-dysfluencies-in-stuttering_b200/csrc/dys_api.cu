@@ -33,10 +33,12 @@ int env_int(const char* name, int dflt) {
 }
 // Sub-batch caps: how many clip instances / denoise chunks share one scratch arena per launch group.
 // Large groups keep the last wave of CTAs full (measured on B200, 10k 3-s clips: 45.9 ms per pass at
-// 1024/1024, 42.6 ms at 4096/4096, 41.9 ms unbounded); the arena is additionally bounded in bytes.
-int feat_cap() { return env_int("DYS_FEAT_SUBBATCH", 8192); }
-int nr_cap() { return env_int("DYS_NR_SUBBATCH", 4096); }
-size_t scratch_budget() { return size_t(env_int("DYS_SCRATCH_MB", 8192)) << 20; }
+// 1024/1024, 42.6 ms at 4096/4096, 41.9 ms unbounded in round 1; round 2: 29.83 ms with 8 GiB of scratch = 3 launch
+// groups per kernel, 29.59 ms with 16 GiB, 29.50 ms with 32 GiB = one group); the arena is additionally bounded in
+// bytes.  The default budget is sized for the 180 GB of a B200: a 10 000-clip batch asks for 27 GB of workspace.
+int feat_cap() { return env_int("DYS_FEAT_SUBBATCH", 32768); }
+int nr_cap() { return env_int("DYS_NR_SUBBATCH", 16384); }
+size_t scratch_budget() { return size_t(env_int("DYS_SCRATCH_MB", 32768)) << 20; }
 int sub_count(size_t per_item, int cap, int64_t total) {
     const size_t by_bytes = std::max<size_t>(1, scratch_budget() / std::max<size_t>(per_item, 1));
     return int(std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(cap, total), int64_t(by_bytes))));
