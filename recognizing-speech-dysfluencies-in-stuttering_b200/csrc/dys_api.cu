@@ -88,7 +88,10 @@ int run_features(const DeviceTables& tb, const ClipView& cv, int inst_begin, int
     const int n_inst_total = inst_end - inst_begin;
     if (n_inst_total <= 0) return DYS_OK;
     const size_t per = feat_scratch_bytes(1, t_max);
-    int n_sub = int(std::min<size_t>(avail / per, size_t(sub_count(per, cap, n_inst_total))));
+    // the wanted group first (it fits exactly when the caller allocated dys_workspace_bytes()), the per-item estimate only
+    // for smaller workspaces: the estimate rounds every array up separately and would cut a 10 000-clip group to 9 998 + 2
+    int n_sub = sub_count(per, cap, n_inst_total);
+    if (feat_scratch_bytes(n_sub, t_max) > avail) n_sub = int(std::min<size_t>(avail / per, size_t(n_sub)));
     if (n_sub < 1) { set_error("workspace too small for one clip"); return DYS_ERR_WORKSPACE; }
     while (n_sub > 1 && feat_scratch_bytes(n_sub, t_max) > avail) --n_sub;
     FeatScratch sc;
@@ -311,7 +314,8 @@ int features_raw_clean_impl(const float* d_audio, const int16_t* d_pcm, const in
         const size_t avail = main_bytes - L.scratch_off;
         const size_t per = nr_scratch_bytes(1, L.ta_max);
         const int64_t n_items = int64_t(n_clips) * L.cpc;
-        int n_sub = int(std::min<size_t>(avail / per, size_t(sub_count(per, nr_cap(), n_items))));
+        int n_sub = sub_count(per, nr_cap(), n_items);
+        if (nr_scratch_bytes(n_sub, L.ta_max) > avail) n_sub = int(std::min<size_t>(avail / per, size_t(n_sub)));
         if (n_sub < 1) { set_error("workspace too small for one denoise chunk"); return DYS_ERR_WORKSPACE; }
         while (n_sub > 1 && nr_scratch_bytes(n_sub, L.ta_max) > avail) --n_sub;
         NrScratch sc;
