@@ -10,11 +10,14 @@
 // turns float32-level errors into LSB flips.
 //
 //   k_nr_stft_mag  : one warp per frame, 512-point complex fp64 FFT + real split -> complex spectrum D and |D|
-//                    [frames x 513 each]
-//   k_nr_iir_mask  : one thread per (chunk, bin), sequential in time: forward IIR (only check-points
-//                    kept), closed-form zero tail, backward IIR with the forward state re-derived in
-//                    reverse, sigmoid, and the 7-tap time smoothing of the mask through a register
-//                    window -> time-smoothed mask, in place of |D|.  NaN (0/0) raises the clip's fallback flag
+//                    [frames x 513 each]; PCM-16 or float32 samples.  Also the FORWARD half of filtfilt: every warp
+//                    keeps Horner sums of b |D| r^k over its frames, one 513-value row per CTA (64 or 256 frames)
+//   k_nr_iir_mask  : one thread per (chunk, bin), sequential in time: chains the CTA rows into the forward
+//                    state at the interval ends (no forward sweep over |D|), closed-form zero tail, backward
+//                    IIR with the forward state re-derived in reverse between those check-points, sigmoid, and the
+//                    7-tap time smoothing of the mask through a register window -> time-smoothed mask, in place of
+//                    |D|.  NaN (0/0) raises the clip's fallback flag.  <true>: rows through a cp.async.bulk.tensor
+//                    ring (opt-in, measured slower)
 //   k_nr_apply_ola : one warp per frame: 33-tap frequency smoothing of the mask row (two cascaded 17-bin
 //                    running sums in registers, 16 bins per lane, halos through the warp's shared-memory
 //                    tile), stored spectrum * mask, inverse FFT, synthesis window; the CTA overlap-adds its

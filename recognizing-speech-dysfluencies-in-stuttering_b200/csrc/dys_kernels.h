@@ -85,7 +85,7 @@ cudaError_t launch_qc(const DeviceTables& tb, const ClipView& cv, float* out, vo
 struct NrScratch {
     double* mag;       // [n_items][ta_max][kNrBinsPad]   |STFT|, then (in place) the time-smoothed sigmoid mask
     double2* spec;     // [n_items][ta_max][kNrBinsPad]   complex STFT (read back when the mask is applied)
-    double* part;      // [n_items][n_seg_max][kNrBinsPad] forward-IIR sums of every 64-frame interval (k_nr_stft_mag -> k_nr_iir_mask)
+    double* part;      // [n_items][n_seg_max][kNrBinsPad] forward-IIR sums, one row per CTA of k_nr_stft_mag (64 or 256 frames) -> k_nr_iir_mask
     int ta_max;
     int n_seg_max;
 };
