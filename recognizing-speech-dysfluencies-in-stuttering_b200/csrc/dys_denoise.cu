@@ -264,7 +264,7 @@ k_nr_stft_mag(const DeviceTables tb, const ClipView cv, int cpc, int item0, NrSc
                                 [&](auto iq, const double2 xq) {
                                     constexpr int q = decltype(iq)::value;
                                     srow[lane + 32 * q] = xq;
-const double m = sqrt(xq.x * xq.x + xq.y * xq.y);
+                                    const double m = sqrt(xq.x * xq.x + xq.y * xq.y);
                                     row[lane + 32 * q] = m;
                                     acc[q] = fma(r8, acc[q], iir_b * m);
                                 }, &nyq);
