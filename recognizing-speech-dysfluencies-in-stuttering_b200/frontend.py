@@ -876,8 +876,18 @@ def build_feature_cache(paths: Sequence[str], overwrite: bool = False, io_thread
                 vec_raw[stem] = raw[i]
                 jobs.append(pool.submit(np.save, files_of(stem)[1], raw[i]))
         if from_wav:                                   # the clean vector of an existing WAV is the feature vector OF THAT WAV
-            pcms = [wavio.read_wav_pcm16(files_of(s)[0])[0] for s in from_wav]
-            cl = extract_features_batch(pcms).cpu().numpy()
+            wavs = []
+            for s_ in from_wav:
+                try:
+                    wavs.append(wavio.read_wav_pcm16(files_of(s_)[0])[0])     # the reference's own WAVs: mono PCM-16, kept 16-bit
+                except Exception:  # noqa: BLE001 - a foreign file: read it like load_audio would; unreadable -> the raw clip
+                    y_, _ = load_audio(files_of(s_)[0])                       # (pipeline1.py:385-387 falls back to the raw file)
+                    wavs.append(first[s_] if y_ is None else y_)
+            if _all_int16(wavs):
+                cl = extract_features_batch(wavs).cpu().numpy()
+            else:                                                             # mixed dtypes: float32 of q / 32768 gives the same bits
+                cl = extract_features_batch([w.astype(np.float32) / np.float32(32768.0) if w.dtype == np.int16 else w
+                                             for w in wavs]).cpu().numpy()
             for i, stem in enumerate(from_wav):
                 vec_clean[stem] = cl[i]
                 jobs.append(pool.submit(np.save, files_of(stem)[2], cl[i]))
