@@ -331,3 +331,30 @@ print('tma ok')
     env = dict(os.environ, DYS_IIR_TMA="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "tma ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_full_size_properties_of_the_new_entry_points(fe, pkg, synth, torch_cuda):
+    """Size-independent properties at the bench configuration (10 000 clips): PCM-16 == float32 of q / 32768 bit for bit;
+    the rate converter is linear, shift-free in its length rule and independent of batch composition."""
+    torch = torch_cuda
+    lib = pkg._lib.load()
+    base = torch.from_numpy(np.stack([owav.quantize_pcm16(synth.synth_clip(i)) for i in range(50)])).cuda()
+    Q = base.repeat(200, 1)                                               # 10 000 x 48 000 int16
+    r16, c16, s16 = fe.extract_features_batch(Q, denoise=True, return_status=True)
+    r32, c32, s32 = fe.extract_features_batch(Q.float() / 32768.0, denoise=True, return_status=True)
+    assert torch.equal(r16, r32) and torch.equal(c16, c32) and torch.equal(s16, s32) and not s16.any()
+    assert torch.equal(r16.reshape(200, 50, 149), r16[:50].expand(200, 50, 149))
+    # rate converter: length rule for a sweep of lengths, linearity, batch independence
+    for n in (1, 2, 440, 441, 442, 66149, 66150, 66151, 222222):
+        assert lib.dys_resampled_length(n, 22050) == -(-n * 320 // 441)
+    rng = np.random.default_rng(9)
+    x = (0.3 * rng.standard_normal(66150)).astype(np.float32)
+    y = (0.3 * rng.standard_normal(66150)).astype(np.float32)
+    rx, ry, rz = fe.resample_to_16k([x, y, (0.5 * x + 0.25 * y).astype(np.float32)], 22050)
+    np.testing.assert_allclose(rz, 0.5 * rx + 0.25 * ry, atol=2e-6, rtol=0)
+    many = fe.resample_to_16k([x] * 3 + [y[:1000]] + [x] * 2500, 22050)    # 2 504 clips, mixed lengths
+    assert all(np.array_equal(many[i], rx) for i in (0, 1, 2, 4, 1000, 2503))
+    np.testing.assert_array_equal(many[3], fe.resample_to_16k([y[:1000]], 22050)[0])
+    # a constant input comes out as the same constant away from the edges (unit DC gain of the low-pass)
+    dc = fe.resample_to_16k([np.full(20000, 0.25, np.float32)], 22050)[0]
+    np.testing.assert_allclose(dc[300:-300], 0.25, atol=2e-6, rtol=0)
