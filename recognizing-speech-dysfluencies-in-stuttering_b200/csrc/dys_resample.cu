@@ -167,6 +167,53 @@ struct RsParams {
     int up, down;
 };
 
+// One group of 16 output phases for kP periods of this lane (period stride xstride input samples / ostride output samples):
+// software pipeline -- the loads of tap i + 1 are issued before the kP x 16 FMAs of tap i.
+template <typename TIn, int kP>
+__device__ __forceinline__ void rs_group(const TIn* __restrict__ xa, int xstride, const float4* __restrict__ c4, int wl,
+                                         float* __restrict__ dst, long long m0, long long ostride, long long n_out) {
+    constexpr float kScale = std::is_same<TIn, int16_t>::value ? (1.0f / 32768.0f) : 1.0f;   // PCM-16: value = q / 32768 (exact)
+    float acc[kP][kGroup];
+#pragma unroll
+    for (int h = 0; h < kP; ++h)
+#pragma unroll
+        for (int k = 0; k < kGroup; ++k) acc[h][k] = 0.f;
+    float4 q0 = c4[0], q1 = c4[1], q2 = c4[2], q3 = c4[3];
+    TIn r[kP];
+#pragma unroll
+    for (int h = 0; h < kP; ++h) r[h] = xa[h * xstride];
+    for (int i = 0; i < wl; ++i) {
+        const int nx = min(i + 1, wl - 1);
+        const float4 n0 = c4[4 * nx], n1 = c4[4 * nx + 1], n2 = c4[4 * nx + 2], n3 = c4[4 * nx + 3];
+        TIn rn[kP];
+#pragma unroll
+        for (int h = 0; h < kP; ++h) rn[h] = xa[h * xstride + nx];
+        const float w[kGroup] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+#pragma unroll
+        for (int h = 0; h < kP; ++h) {
+            const float v = float(r[h]) * kScale;
+#pragma unroll
+            for (int k = 0; k < kGroup; ++k) acc[h][k] = fmaf(w[k], v, acc[h][k]);
+        }
+        q0 = n0; q1 = n1; q2 = n2; q3 = n3;
+#pragma unroll
+        for (int h = 0; h < kP; ++h) r[h] = rn[h];
+    }
+#pragma unroll
+    for (int h = 0; h < kP; ++h) {
+        const long long m = m0 + h * ostride;
+        if (m + kGroup <= n_out && ((reinterpret_cast<uintptr_t>(dst + m) & 15u) == 0)) {
+#pragma unroll
+            for (int k = 0; k < kGroup; k += 4)
+                *reinterpret_cast<float4*>(dst + m + k) = make_float4(acc[h][k], acc[h][k + 1], acc[h][k + 2], acc[h][k + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kGroup; ++k)
+                if (m + k < n_out) dst[m + k] = acc[h][k];
+        }
+    }
+}
+
 // grid (clips, tiles of 64 periods); up to 8 warps; dynamic smem: [mbarriers 128 B][input tile, kept in the input's own
 // type: 16-bit PCM tiles are half the size, which doubles the resident warps][warps x (wl x 16) coefficients].
 // Lane r of a warp owns periods r and r + 32 of the tile: 2 x 16 accumulators, so every 16-byte broadcast of
@@ -216,11 +263,12 @@ k_resample(const TIn* __restrict__ in, const int64_t* __restrict__ in_starts, co
     }
     __syncthreads();                                                 // barriers initialised, hand-written part in place
     if (ahi > alo) mbar_wait(&bars[0], 0);
-    constexpr float kScale = std::is_same<TIn, int16_t>::value ? (1.0f / 32768.0f) : 1.0f;   // PCM-16: value = q / 32768 (exact)
     float* dst = out + out_starts[c];
+    // the clip's last tile often holds fewer than 33 periods (a 3-s clip: 64 + 64 + 22): then only the lanes' first period
+    // exists and the second accumulator set is skipped
+    const bool two = (per0 + 32) * P.up2 < n_out;
     unsigned phase = 0;
     for (int g = warp; g < P.n_groups; g += n_warps, phase ^= 1u) {
-        float4* c4 = reinterpret_cast<float4*>(ct);
         __syncwarp();                                                // every lane is done with the previous table
         if (lane == 0) {
             fence_proxy_async();
@@ -228,37 +276,10 @@ k_resample(const TIn* __restrict__ in, const int64_t* __restrict__ in_starts, co
             bulk_copy_g2s(ct, expanded + size_t(g) * P.wl * kGroup, unsigned(P.wl * kGroup * 4), &bars[1 + warp]);
         }
         const TIn* xa = xt + lane * P.down2 + (__ldg(wstart + g) + P.half);     // window of period `lane` for this group
-        const TIn* xb = xa + 32 * P.down2;                                      // ... and of period lane + 32
-        float acc[2][kGroup];
-#pragma unroll
-        for (int k = 0; k < kGroup; ++k) { acc[0][k] = 0.f; acc[1][k] = 0.f; }
         mbar_wait(&bars[1 + warp], phase);
-        // software pipeline: the loads of tap i + 1 are issued before the 32 FMAs of tap i
-        float4 q0 = c4[0], q1 = c4[1], q2 = c4[2], q3 = c4[3];
-        TIn ra = xa[0], rb = xb[0];
-        for (int i = 0; i < P.wl; ++i) {
-            const int nx = min(i + 1, P.wl - 1);
-            const float4 n0 = c4[4 * nx], n1 = c4[4 * nx + 1], n2 = c4[4 * nx + 2], n3 = c4[4 * nx + 3];
-            const TIn na = xa[nx], nb = xb[nx];
-            const float va = float(ra) * kScale, vb = float(rb) * kScale;
-            const float w[kGroup] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
-#pragma unroll
-            for (int k = 0; k < kGroup; ++k) { acc[0][k] = fmaf(w[k], va, acc[0][k]); acc[1][k] = fmaf(w[k], vb, acc[1][k]); }
-            q0 = n0; q1 = n1; q2 = n2; q3 = n3; ra = na; rb = nb;
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const long long m0 = (per0 + lane + 32 * h) * P.up2 + (long long)g * kGroup;
-            if (m0 + kGroup <= n_out && ((reinterpret_cast<uintptr_t>(dst + m0) & 15u) == 0)) {
-#pragma unroll
-                for (int k = 0; k < kGroup; k += 4)
-                    *reinterpret_cast<float4*>(dst + m0 + k) = make_float4(acc[h][k], acc[h][k + 1], acc[h][k + 2], acc[h][k + 3]);
-            } else {
-#pragma unroll
-                for (int k = 0; k < kGroup; ++k)
-                    if (m0 + k < n_out) dst[m0 + k] = acc[h][k];
-            }
-        }
+        const long long m0 = (per0 + lane) * P.up2 + (long long)g * kGroup;
+        if (two) rs_group<TIn, 2>(xa, 32 * P.down2, reinterpret_cast<const float4*>(ct), P.wl, dst, m0, 32LL * P.up2, n_out);
+        else rs_group<TIn, 1>(xa, 32 * P.down2, reinterpret_cast<const float4*>(ct), P.wl, dst, m0, 32LL * P.up2, n_out);
     }
 }
 
