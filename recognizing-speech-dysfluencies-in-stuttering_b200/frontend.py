@@ -431,6 +431,19 @@ def extract_features_host(audio: torch.Tensor, denoise: bool = True, prop_decrea
     return (out_raw, out_clean) if denoise else out_raw
 
 
+_pinned_cache: dict = {}
+
+
+def _pinned_rows(which: str, rows: int) -> torch.Tensor:
+    """Grow-only pinned float32 [rows, 149] staging for results (pinning a fresh buffer per call costs a millisecond or
+    two of cudaHostRegister); only used under _host_lock."""
+    buf = _pinned_cache.get(which)
+    if buf is None or buf.shape[0] < rows:
+        buf = torch.empty((max(rows, 1), FEATURE_LEN), dtype=torch.float32).pin_memory()
+        _pinned_cache[which] = buf
+    return buf[:rows]
+
+
 class PackedClips:
     """Ragged host clips packed once into ONE pinned buffer, in length-sorted order (clips of similar length share
     launch groups and waves of CTAs), ready to be streamed to the GPU chunk by chunk.  ``order[j]`` is the caller's index
@@ -480,9 +493,9 @@ def extract_features_host_packed(packed: PackedClips, denoise: bool = True, prop
     lib = _lib.load()
     flag = 1 if denoise else 0
     n_comp = max(1, min(int(compute_streams), 4))
-    srt_raw = torch.empty((B, FEATURE_LEN), dtype=torch.float32).pin_memory()     # rows in packed (sorted) order
-    srt_clean = torch.empty((B, FEATURE_LEN), dtype=torch.float32).pin_memory() if denoise else None
     with torch.cuda.device(dev), _host_lock:
+        srt_raw = _pinned_rows("raw", B)                                          # rows in packed (sorted) order
+        srt_clean = _pinned_rows("clean", B) if denoise else None
         _lib.check(lib.dys_init(), "dys_init")
         cur = torch.cuda.current_stream(dev)
         streams = _host_streams(dev, 1 + n_comp)
