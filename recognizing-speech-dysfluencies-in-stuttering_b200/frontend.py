@@ -545,10 +545,10 @@ def extract_features_host_packed(packed: PackedClips, denoise: bool = True, prop
         for s_ in comp:
             cur.wait_stream(s_)
         cur.synchronize()
-    idx = torch.from_numpy(packed.order)
-    out_raw[idx] = srt_raw                                                        # back to the caller's order (host, 149 floats per clip)
-    if denoise:
-        out_clean[idx] = srt_clean
+        idx = torch.from_numpy(packed.order)
+        out_raw[idx] = srt_raw                                                    # back to the caller's order (host, 149 floats per clip)
+        if denoise:
+            out_clean[idx] = srt_clean
     return (out_raw, out_clean) if denoise else out_raw
 
 
