@@ -363,9 +363,10 @@ def extract_features_host(audio: torch.Tensor, denoise: bool = True, prop_decrea
         return (out_raw, out_clean) if denoise else out_raw
     if chunk_clips is None:
         # float32 samples: the copy is the bottleneck, small chunks keep the kernels close behind it; PCM-16 halves the copy
-        # and the kernels become the bottleneck, which larger launch groups serve better (measured, 10 000 3-s clips:
-        # 33.9 ms at 400 clips per chunk, 32.5 ms at 625 - 1250; tools/sweep_e2e_pcm.py)
-        chunk_clips = max(1, (800 * 48000) // max(n, 1)) if pcm_in else max(1, (400 * 48000) // max(n, 1))
+        # and the kernels become the bottleneck, which larger launch groups serve better (measured, 10 000 3-s clips,
+        # tools/sweep_e2e_pcm.py / sweep_e2e_f32.py: PCM-16 33.9 ms at 400 clips per chunk, 31.7 at 592, 32.0 at 800, 32.3 at
+        # 1184; float32 36.2 ms at 296, 36.8 at 400, 37.6 at 888)
+        chunk_clips = max(1, (592 * 48000) // max(n, 1)) if pcm_in else max(1, (296 * 48000) // max(n, 1))
     chunk = max(1, min(int(chunk_clips), B))
     head = [max(1, chunk // 4), max(1, chunk // 2)] if B >= 3 * chunk else []      # short first copies: kernels start early
     sizes, left = list(head), B - sum(head)
@@ -481,7 +482,7 @@ def extract_features_host_packed(packed: PackedClips, denoise: bool = True, prop
         return (out_raw, out_clean) if denoise else out_raw
     esz = 2 if packed.pcm16 else 4
     if chunk_samples is None:
-        chunk_samples = (800 if packed.pcm16 else 400) * 48000                   # see extract_features_host
+        chunk_samples = (592 if packed.pcm16 else 296) * 48000                   # see extract_features_host
     ends = packed.starts + ((packed.lengths.astype(np.int64) + 3) & ~3)          # padded extent of every clip in the buffer
     cuts, c0 = [], 0                                                              # (first clip, end clip, first sample, end sample)
     while c0 < B:

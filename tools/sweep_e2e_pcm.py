@@ -9,8 +9,8 @@ torch.cuda.set_device(0)
 base = torch.from_numpy(pkg.synth.synth_batch(100))
 host = (base.repeat(100, 1) * 32768.0 * 0.9).round().clamp(-32768, 32767).to(torch.int16).pin_memory()
 raw = torch.empty((10000, 149)).pin_memory(); clean = torch.empty((10000, 149)).pin_memory()
-for streams in (2, 3, 4):
-    for chunk in (400, 625, 1000, 1250, 2000, 2500, 5000):
+for streams in (3,):
+    for chunk in (592, 740, 800, 888, 1036, 1184, 1480):
         for _ in range(3):
             fe.extract_features_host(host, chunk_clips=chunk, out_raw=raw, out_clean=clean, compute_streams=streams)
         torch.cuda.synchronize(); t0 = time.perf_counter()
