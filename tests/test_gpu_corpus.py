@@ -361,7 +361,7 @@ def test_full_size_properties_of_the_new_entry_points(fe, pkg, synth, torch_cuda
 
 
 def test_big_launch_groups_with_many_intervals_per_chunk(fe, synth, torch_cuda):
-    """Gate geometry coverage: a launch group of >= 592 chunks uses 256-frame CTAs in k_nr_stft_mag, so a long clip
+    """Gate geometry coverage: a launch group of >= 888 chunks uses 256-frame CTAs in k_nr_stft_mag, so a long clip
     chains several forward-IIR intervals per chunk (a 3-s clip has only one).  Long clips in a big group must give the
     same PCM as the same clips alone (64-frame CTAs, other interval boundaries would differ only in float64 rounding
     that never reaches the PCM) and as the oracle."""
@@ -369,22 +369,22 @@ def test_big_launch_groups_with_many_intervals_per_chunk(fe, synth, torch_cuda):
     n_long, L = 150, 163840                                   # 10.2 s clips: 644 active frames -> 3 intervals of 256 frames
     base = np.concatenate([synth.synth_clip(60 + i) for i in range(4)])[:L]
     X = torch.from_numpy(np.stack([base * np.float32(0.3 + 0.004 * i) for i in range(n_long)]))
-    # 150 long clips + 450 short ones = 600 chunks in one launch group
-    shorts = [synth.synth_clip(200 + (i % 7), 6000 + 13 * i) for i in range(450)]
+    # 150 long clips + 750 short ones = 900 chunks in one launch group
+    shorts = [synth.synth_clip(200 + (i % 7), 6000 + 7 * i) for i in range(750)]
     clips = [X[i].numpy() for i in range(n_long)] + shorts
     raw, clean, st, pcm = fe.extract_features_batch(clips, denoise=True, return_status=True, return_pcm=True)
     assert not st.cpu().numpy().any()
-    for i in (0, 77, 149, 150, 599):
+    for i in (0, 77, 149, 150, 899):
         r1, c1, _, p1 = fe.extract_features_batch([clips[i]], denoise=True, return_status=True, return_pcm=True)
         assert torch.equal(p1[0], pcm[i]) and torch.equal(c1[0], clean[i]) and torch.equal(r1[0], raw[i]), i
     q = oden.clean_audio(clips[77])
     assert np.array_equal(pcm[77].cpu().numpy(), q)
     # chunked clips (> 600 000 samples: 2 chunks each, every frame of a chunk active -> 11 intervals of 256) in a big group
     long2 = np.concatenate([synth.synth_clip(300 + i) for i in range(14)])[:650000]
-    many = [np.ascontiguousarray(long2 * np.float32(0.5 + 0.001 * i)) for i in range(300)]        # 600 chunks
+    many = [np.ascontiguousarray(long2 * np.float32(0.5 + 0.001 * i)) for i in range(450)]        # 900 chunks
     raw2, clean2, st2, pcm2 = fe.extract_features_batch(many, denoise=True, return_status=True, return_pcm=True)
     assert not st2.cpu().numpy().any()
-    for i in (0, 299):
+    for i in (0, 449):
         _, c1, _, p1 = fe.extract_features_batch([many[i]], denoise=True, return_status=True, return_pcm=True)
         assert torch.equal(p1[0], pcm2[i]) and torch.equal(c1[0], clean2[i]), i
     assert np.array_equal(pcm2[0].cpu().numpy(), oden.clean_audio(many[0]))
