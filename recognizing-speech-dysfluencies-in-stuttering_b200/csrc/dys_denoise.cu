@@ -50,11 +50,11 @@ namespace {
 
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
-// Launch groups with at least this many chunks fill the machine three times over with ONE CTA per chunk: k_nr_stft_mag then
+// Launch groups with at least this many chunks fill the machine twice over with ONE CTA per chunk: k_nr_stft_mag then
 // gives a CTA 256 frames instead of 64 (its 24 KB of tables are loaded once per CTA: -2 %) and k_nr_apply_ola 24 rounds
 // instead of 8 (no frames transformed twice at CTA seams: -1.6 %).  Smaller groups keep the short CTAs: a single clip's
 // latency is set by how many SMs its frames spread over.
-constexpr int kBigGroup = 888;
+constexpr int kBigGroup = 592;
 constexpr int kFramesPerCtaSmall = 64, kFramesPerCtaBig = 256;   // powers of two: the check-point tests of the sweep are masks
 constexpr int kIirSegShift = 6;
 constexpr int kIirSeg = 1 << kIirSegShift;           // frames per forward-IIR interval = check-point spacing of the backward sweep
@@ -869,9 +869,11 @@ cudaError_t launch_denoise(const DeviceTables& tb, const ClipView& cv, float* cl
     if (cudaError_t e = ensure_dynamic_smem<kK_nr_stft_mag + 32>(k_nr_stft_mag<true>, int(sizeof(MagSmem)))) return e;
     if (cudaError_t e = ensure_dynamic_smem<kK_nr_apply_ola>(k_nr_apply_ola<kApplyWarps>, int(sizeof(ApplySmem<kApplyWarps>)))) return e;
     if (sc.ta_max > kIirMaxSeg << kIirSegShift) return cudaErrorInvalidValue;
-    // One CTA per chunk ("big") saves table loads and seam frames; below three waves of resident CTAs the 64-frame CTAs
-    // win because they fill the tail (measured per clip, tools/group_geometry_probe.py: 600 chunks 3.44 vs 3.66 us, 800:
-    // 3.24 vs 3.28, 888: 3.16 vs 3.10, 2 500: 3.05 vs 2.99, 10 000: 3.04 vs 2.97).  DYS_GATE_BIG=0/1 forces a geometry.
+    // One CTA per chunk ("big") saves table loads and seam frames.  Alone, a batch below three waves of resident CTAs runs
+    // a little faster with the 64-frame CTAs (tools/group_geometry_probe.py, per clip: 600 chunks 3.44 vs 3.66 us, 800: 3.24
+    // vs 3.28, 888: 3.16 vs 3.10, 2 500: 3.05 vs 2.99, 10 000: 3.04 vs 2.97) -- but inside the host streaming path, where
+    // three streams fill each other's tails, 592-clip chunks take 31.7 ms per 10 000 clips with one CTA per chunk and 32.7 ms
+    // with the short CTAs, so the threshold stays at two waves.  DYS_GATE_BIG=0/1 forces a geometry.
     bool big = n_items >= kBigGroup;
     static const int forced = [] { const char* v = std::getenv("DYS_GATE_BIG"); return v ? (v[0] == '1' ? 1 : (v[0] == '0' ? 0 : -1)) : -1; }();
     if (forced >= 0) big = forced == 1;

@@ -361,7 +361,7 @@ def test_full_size_properties_of_the_new_entry_points(fe, pkg, synth, torch_cuda
 
 
 def test_big_launch_groups_with_many_intervals_per_chunk(fe, synth, torch_cuda):
-    """Gate geometry coverage: a launch group of >= 888 chunks uses 256-frame CTAs in k_nr_stft_mag, so a long clip
+    """Gate geometry coverage: a launch group of >= 592 chunks uses 256-frame CTAs in k_nr_stft_mag, so a long clip
     chains several forward-IIR intervals per chunk (a 3-s clip has only one).  Long clips in a big group must give the
     same PCM as the same clips alone (64-frame CTAs, other interval boundaries would differ only in float64 rounding
     that never reaches the PCM) and as the oracle."""
