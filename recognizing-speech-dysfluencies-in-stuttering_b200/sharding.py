@@ -17,6 +17,16 @@ def shard_range(n_items: int, rank: int, world: int) -> tuple[int, int]:
     return (rank * n_items) // world, ((rank + 1) * n_items) // world
 
 
+def spread_device_index(local_rank: int, world: int, n_visible: int) -> int:
+    """GPU for a rank when fewer ranks than GPUs run on one box: alternate between the two halves of the box (rank 0 ->
+    GPU 0, rank 1 -> GPU G/2, rank 2 -> GPU 1, ...).  On 8-GPU HGX-style hosts the halves hang off different host
+    bridges, and host-to-device streaming is bound by what one bridge delivers (measured on this pool: 4 ranks on GPUs
+    0-3 get 28.8 GB/s each, on GPUs 0, 4, 1, 5 they get 52.8 GB/s).  Identity when all GPUs are used."""
+    if not (1 < world < n_visible) or n_visible % 2:
+        return local_rank
+    return (local_rank % 2) * (n_visible // 2) + local_rank // 2
+
+
 def sliding_windows(n_samples: int, win: int = 48000, hop: int = 24000):
     """Window starts of the long-form segmenter (BASELINE config 4: win 48 000 / hop 24 000 ->
     2399 windows per hour).  Each window is an independent clip for the feature function."""

@@ -110,6 +110,13 @@ def test_sharding_and_windows(pkg):
     assert sh.sliding_windows(47999) == []
 
 
+def test_rank_to_gpu_spreading(pkg):
+    f = pkg.sharding.spread_device_index
+    assert [f(r, 4, 8) for r in range(4)] == [0, 4, 1, 5] and [f(r, 2, 8) for r in range(2)] == [0, 4]
+    assert [f(r, 8, 8) for r in range(8)] == list(range(8)) and f(0, 1, 8) == 0 and [f(r, 2, 3) for r in range(2)] == [0, 1]
+    assert sorted(f(r, 6, 8) for r in range(6)) == [0, 1, 2, 4, 5, 6]
+
+
 def test_wav_io_round_trip(pkg, tmp_path):
     q = (np.random.default_rng(0).integers(-32768, 32767, 1000)).astype(np.int16)
     p = tmp_path / "a.wav"
